@@ -1,0 +1,214 @@
+/*
+ * stcgan_b200 -- C ABI of the B200-native ST-CGAN hot path.
+ *
+ * The reference (nhchiu/Shadow-Removal-ISTD) is pure Python and has NO FFI/plugin layer:
+ * its hot path calls torch.nn ops which dispatch to cuDNN/oneDNN.
+ * The drop-in seam is therefore the nn.Module contract (python package `stcgan_b200`);
+ * this header is the boundary *below* that seam: every piece of arithmetic the reference
+ * obtains from torch on this path is an entry point here, on raw device pointers.
+ * Each entry point cites the reference call site(s) whose arithmetic it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says `host`;
+ *   - activations are NHWC ("pixel-major"): element (n,h,w,c) of a tensor with pixel pitch
+ *     `ld` lives at ((n*H + h)*W + w)*ld + c; a channel slice of a wider buffer is addressed by
+ *     offsetting the base pointer and keeping the wide `ld` (that is how U-Net skip
+ *     concatenations are produced in place instead of by a copy);
+ *   - `dtype` selects the activation/packed-weight element type: STCGAN_F32 or STCGAN_BF16;
+ *     accumulation is always fp32 (statistics: fp64);
+ *   - packed conv weights are tap-major: Wp[t][n][k], t = kh*4+kw, n = output channel of the
+ *     GEMM, k = reduction channel;  packed weight gradients are G[t][d0][d1] fp32 where
+ *     (d0,d1) are the first two dims of the torch parameter ([Cout,Cin,4,4] for Conv2d,
+ *     [Cin,Cout,4,4] for ConvTranspose2d);
+ *   - every function returns 0 on success, a negative STCGAN_E* code on bad arguments, or a
+ *     positive cudaError_t; nothing throws or exits across this boundary;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - nothing here allocates or retains caller memory; the caller (torch's caching allocator
+ *     in the Python host) owns every buffer.
+ */
+#ifndef STCGAN_B200_H
+#define STCGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STCGAN_ABI_VERSION 1
+
+enum { STCGAN_F32 = 0, STCGAN_BF16 = 1 };
+
+/* error codes */
+enum {
+  STCGAN_OK = 0,
+  STCGAN_EINVAL = -1,      /* bad argument (shape / alignment / enum) */
+  STCGAN_EUNSUPPORTED = -2 /* shape not supported by the selected backend */
+};
+
+/* activation codes (fused into epilogues / BN apply) */
+enum { STCGAN_ACT_NONE = 0, STCGAN_ACT_LEAKY = 1, STCGAN_ACT_RELU = 2, STCGAN_ACT_TANH = 3, STCGAN_ACT_SIGMOID = 4 };
+
+/* gather geometries of the implicit GEMM  out[p, n] = sum_t sum_k in[gather_t(p), k] * Wp[t][n][k] */
+enum {
+  STCGAN_GEOM_WIN_S2 = 0,      /* 4x4 window, stride 2, pad 1 : Conv2d(4,2,1) forward; ConvTranspose2d(4,2,1) dgrad */
+  STCGAN_GEOM_WIN_S1 = 1,      /* 4x4 window, stride 1, pad 1 : Conv2d(4,1,1) forward */
+  STCGAN_GEOM_WIN_S1_FLIP = 2, /* 4x4 window, stride 1, pad 2, flipped taps : Conv2d(4,1,1) dgrad */
+  STCGAN_GEOM_PARITY = 3       /* 4 output-parity classes x 2x2 taps : ConvTranspose2d(4,2,1) forward; Conv2d(4,2,1) dgrad */
+};
+
+/* compute back-ends */
+enum {
+  STCGAN_BACKEND_FFMA = 0, /* CUDA-core fp32-accumulate tiles: any shape, both dtypes (the fp32 mode and thin layers) */
+  STCGAN_BACKEND_TC = 1    /* tcgen05 + TMEM + TMA implicit GEMM, bf16 only, K%64==0, Nout%64==0 */
+};
+
+/* ---- library ---------------------------------------------------------------------------- */
+int stcgan_abi_version(void);
+/* compiled arch string, e.g. "sm_100a" */
+const char* stcgan_arch(void);
+/* human-readable text for a return code of any function below */
+const char* stcgan_error_string(int code);
+/* number of kernels launched by this library since the last reset (host counter) */
+int64_t stcgan_launch_count(void);
+void stcgan_launch_count_reset(void);
+
+/* ---- convolutions as tap-GEMMs ------------------------------------------------------------
+ * replaces: nn.Conv2d(k=4,s=2,p=1) forward/backward  src/models/stcgan_g.py:85-86, stcgan_d.py:22-23,33-35
+ *           nn.Conv2d(k=4,s=1,p=1) forward/backward  src/models/stcgan_d.py:43-44,49-50
+ *           nn.ConvTranspose2d(k=4,s=2,p=1) fwd/bwd   src/models/stcgan_g.py:93-95,100-102,107-109
+ * (the reference reaches cuDNN/oneDNN through ATen for all of them).
+ *
+ * x    : input  [N, IH, IW, K]   pitch ldx      (dtype)
+ * wp   : packed weights [16][Nout][K]            (dtype)
+ * bias : optional fp32 [Nout] (NULL = none)
+ * y    : output [N, OH, OW, Nout] pitch ldy      (dtype), or, if out_nchw_f32 != 0, a float tensor
+ *        [N, Nout, OH, OW] (used for the generator's final Tanh output)
+ * act  : epilogue activation applied after bias
+ * IH/IW may be smaller than the window reach implies: out-of-range taps read zeros, which is
+ * also how the reference's odd-size F.pad (stcgan_g.py:126-132) is realised without a copy.
+ */
+int stcgan_tapconv(int geom, int dtype, int backend,
+                   const void* x, int N, int IH, int IW, int K, int ldx,
+                   const void* wp, const float* bias, int act,
+                   void* y, int OH, int OW, int Nout, int ldy, int out_nchw_f32,
+                   void* stream);
+
+/* weight gradient of the same convolutions:  G[t][d0][d1] += sum_p S[p, d0] * L[win_t(p), d1]
+ * S : "small-grid" tensor [N, SH, SW, D0] pitch lds (Conv2d: dY; ConvTranspose2d: the layer input)
+ * L : "large-grid" tensor [N, LH, LW, D1] pitch ldl (Conv2d: the layer input; ConvTranspose2d: dY)
+ * geom : STCGAN_GEOM_WIN_S2 or STCGAN_GEOM_WIN_S1 (window of the *forward* Conv2d, or of the
+ *        ConvTranspose2d seen from its output side)
+ * G accumulates (callers zero it once per backward phase), fp32. */
+int stcgan_tapwgrad(int geom, int dtype, int backend,
+                    const void* S, int N, int SH, int SW, int D0, int lds,
+                    const void* L, int LH, int LW, int D1, int ldl,
+                    float* G, void* stream);
+
+/* ---- weight layout ---------------------------------------------------------------------------
+ * torch parameter W[d0][d1][4][4] fp32  ->  P1[t][d0][d1] and P2[t][d1][d0] in `dtype`
+ * (either output may be NULL).  State-dict layout: src/models/stcgan_g.py:85-109, stcgan_d.py:22-50. */
+int stcgan_pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, void* stream);
+/* packed gradient G[t][d0][d1] fp32 -> torch layout grad[d0][d1][16]; accumulate != 0 adds */
+int stcgan_unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, void* stream);
+
+/* ---- BatchNorm2d + activation -----------------------------------------------------------------
+ * replaces: nn.BatchNorm2d (train/eval) + nn.LeakyReLU(0.2,True) / nn.ReLU(True)
+ *           src/models/stcgan_g.py:87-90, stcgan_d.py:24,36-37,45-46
+ */
+/* per-channel sum / sum-of-squares of y [P pixels x C] (pitch ld) accumulated into fp64 acc[2][C] (caller zeroes) */
+int stcgan_bn_stats(int dtype, const void* y, int64_t P, int C, int ld, double* acc, void* stream);
+/* training: mean/biased var from acc over count P -> mean_invstd[2][C], scale_shift[2][C] (scale = gamma*invstd,
+ * shift = beta - mean*scale); running_mean/var momentum update with unbiased var (NULL = skip).
+ * eval (training == 0): statistics taken from running_mean/var, acc ignored. */
+int stcgan_bn_finalize(const double* acc, int64_t P, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int training,
+                       float* mean_invstd, float* scale_shift, void* stream);
+/* out1 = act1(y*scale + shift) (and optionally out2 = act2(..)) over the cropped region [N, HC, WC] of
+ * y [N, H, W, C]; scale_shift == NULL means identity (layers without BatchNorm).  out2 may be NULL. */
+int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
+                        const float* scale_shift, int HC, int WC,
+                        void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
+/* backward, pass 1: dz = g1*act1'(z) + g2*act2'(z) (z = y*scale+shift, zero outside the crop);
+ * acc[0][c] += sum dz, acc[1][c] += sum dz*xhat   (fp64, caller zeroes) */
+int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy,
+                             const float* scale_shift, const float* mean_invstd, int HC, int WC,
+                             const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
+                             double* acc, void* stream);
+/* backward, pass 2: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))  (training)
+ *                   dy = gamma*invstd*dz (eval) ;  dy = dz (scale_shift == NULL: no BatchNorm)
+ * also dgamma += acc[1], dbeta += acc[0] (by the first block; NULL = skip). */
+int stcgan_bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
+                            const float* scale_shift, const float* mean_invstd, const float* gamma,
+                            int training, int HC, int WC,
+                            const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
+                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, void* stream);
+/* column sums of g [P x C] (pitch ld) added to fp32 out[C]  (bias gradients, stcgan_g.py:93-95, stcgan_d.py:22-23,49-50) */
+int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out, void* stream);
+
+/* ---- tensor layout at the module boundary ------------------------------------------------------
+ * replaces the torch.cat of NCHW inputs (src/cgan.py:281-289, 321-324): up to three NCHW fp32 sources are
+ * gathered into one NHWC tensor of Cpad >= c0+c1+c2 channels (extra channels zero). */
+int stcgan_pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
+                      int N, int H, int W, void* out, int Cpad, void* stream);
+/* gradient of the above for a channel range: grad_nchw[n, c, h, w] (+)= g[n,h,w, coff + c] , c < cn */
+int stcgan_unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn,
+                             float* grad_nchw, int accumulate, void* stream);
+/* NHWC (dtype) -> NCHW fp32 (module outputs, e.g. discriminator logits) and back */
+int stcgan_nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, float* out, void* stream);
+int stcgan_nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, void* stream);
+/* g_nhwc = dout * (1 - out^2) (Tanh backward, stcgan_g.py:97) or dout*out*(1-out) (Sigmoid, stcgan_d.py:52-53), NCHW fp32 in */
+int stcgan_out_act_bwd(int dtype, int act, const float* out_nchw, const float* dout_nchw, int N, int H, int W, int C,
+                       void* g, int ldg, void* stream);
+
+/* ---- losses ---------------------------------------------------------------------------------------
+ * replaces: AdversarialLoss.cal_loss (src/loss.py:79-84: ls==0 -> MSE, ls!=0 -> BCE-with-logits against a scalar
+ * target) and DataLoss (src/loss.py:25-26: L1 mean), forward value AND gradient in one pass, for up to 8 terms
+ * in one launch.  term kinds: 0 = L1(a, b), 1 = MSE(a, target), 2 = BCE-with-logits(a, target).
+ * loss_out[slot] += loss_weight * mean(term);  grad (optional) (+)= weight * d mean(term) / d a.
+ */
+typedef struct stcgan_loss_term {
+  const float* a;      /* prediction / logits, fp32, n elements (any layout: elementwise) */
+  const float* b;      /* L1 target (kind 0), else ignored */
+  float* grad;         /* d/da, may be NULL */
+  int64_t n;
+  float target;        /* scalar label for kinds 1,2 */
+  float weight;        /* gradient weight: grad (+)= weight * d mean(term)/da   (lambda * 0.5 etc.) */
+  int32_t kind;
+  int32_t slot;        /* index into loss_out */
+  int32_t accumulate;  /* grad += instead of = */
+  float loss_weight;   /* value weight: loss_out[slot] += loss_weight * mean(term) */
+} stcgan_loss_term;
+int stcgan_fused_loss(const stcgan_loss_term* host_terms, int nterms, float* loss_out, void* stream);
+
+/* ---- optimiser --------------------------------------------------------------------------------------
+ * replaces torch.optim.Adam(betas, eps=1e-8, no weight decay, no amsgrad) of src/cgan.py:85-90,305,351 as one
+ * multi-tensor launch.  Gradients may be in packed [16][d0][d1] layout (d0 > 0) or torch layout (d0 == 0).
+ * grad_scale multiplies g (1/world for DDP). */
+typedef struct stcgan_adam_tensor {
+  float* p; const float* g; float* m; float* v;
+  int64_t n;
+  int32_t d0, d1;     /* packed-gradient dims, 0 = gradient in parameter layout */
+} stcgan_adam_tensor;
+/* the table lives in DEVICE memory (built once); blocks[] maps each CUDA block to (tensor, chunk).
+ * dev_hyper is a DEVICE array of 8 floats, in/out: {lr, beta1, beta2, eps, grad_scale, steps_done, -, -}.
+ * The call first increments steps_done ON THE DEVICE and derives the bias corrections from it (slots 6,7), then
+ * updates all tensors -- so a captured CUDA graph of the whole train step replays correctly without any
+ * host-side refresh; the host rewrites lr / steps_done only when the schedule or a checkpoint changes them. */
+int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blocks, int nblocks,
+                     float* dev_hyper, void* stream);
+/* elements per block chunk used by stcgan_adam_step (host helper for building dev_blocks) */
+int stcgan_adam_chunk(void);
+
+/* ---- inference post-processing ------------------------------------------------------------------------
+ * replaces `*0.5+0.5` (src/cgan.py:441-442) + utils.float2uint (src/utils.py:65-67) + CHW->HWC transpose
+ * (cgan.py:443-446): u8[n,h,w,c] = (uint8) trunc(clip(v*0.5+0.5, 0, 1) * 255), all in fp32 like numpy. */
+int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream);
+/* plain float2uint on a flat array (known-answer tests) */
+int stcgan_float2uint(const float* in, int64_t n, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STCGAN_B200_H */

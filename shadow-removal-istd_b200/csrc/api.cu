@@ -1,0 +1,202 @@
+// extern "C" surface of libstcgan_b200.so (see include/stcgan_b200.h for the contract).
+#include "common.cuh"
+
+namespace stcgan {
+int64_t g_launches = 0;
+
+// tapconv_ffma.cu
+int tapconv_ffma(const Geom& g, int dtype, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
+                 void* y, int Nout, int ldy, int out_nchw_f32, cudaStream_t st);
+int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int D0, int lds,
+                  const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
+// tapconv_tc.cu
+int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
+               void* y, int Nout, int ldy, cudaStream_t st);
+int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
+                const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
+// bn_act.cu
+int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st);
+int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
+                float momentum, float eps, int training, float* mean_invstd, float* scale_shift, cudaStream_t st);
+int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, int HC, int WC,
+                 void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st);
+int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                      int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
+                      double* acc, cudaStream_t st);
+int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                     const float* gamma, int training, int HC, int WC, const void* g1, int ldg1, int act1,
+                     const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
+                     float* dgamma, float* dbeta, cudaStream_t st);
+int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cudaStream_t st);
+// misc.cu
+int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, cudaStream_t st);
+int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cudaStream_t st);
+int pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
+               int N, int H, int W, void* out, int Cpad, cudaStream_t st);
+int unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn, float* grad,
+                      int accumulate, cudaStream_t st);
+int nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, float* out, cudaStream_t st);
+int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, cudaStream_t st);
+int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, void* g, int ldg,
+                cudaStream_t st);
+int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st);
+int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st);
+int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st);
+int float2uint_hwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
+}  // namespace stcgan
+
+using namespace stcgan;
+
+static bool dtype_ok(int d) { return d == STCGAN_F32 || d == STCGAN_BF16; }
+
+extern "C" {
+
+int stcgan_abi_version(void) { return STCGAN_ABI_VERSION; }
+const char* stcgan_arch(void) { return "sm_100a"; }
+
+const char* stcgan_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == STCGAN_EINVAL) return "stcgan: invalid argument (shape / alignment / enum)";
+  if (code == STCGAN_EUNSUPPORTED) return "stcgan: shape not supported by the selected backend";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "stcgan: unknown error";
+}
+
+int64_t stcgan_launch_count(void) { return g_launches; }
+void stcgan_launch_count_reset(void) { g_launches = 0; }
+
+int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int IH, int IW, int K, int ldx,
+                   const void* wp, const float* bias, int act, void* y, int OH, int OW, int Nout, int ldy,
+                   int out_nchw_f32, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && x && wp && y);
+  STCGAN_REQUIRE(N >= 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && K > 0 && Nout > 0 && ldx >= K);
+  STCGAN_REQUIRE(out_nchw_f32 || ldy >= Nout);
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_SIGMOID);
+  Geom g;
+  if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
+  if (N == 0) return 0;
+  if (backend == STCGAN_BACKEND_TC) {
+    if (dtype != STCGAN_BF16 || out_nchw_f32) return STCGAN_EUNSUPPORTED;
+    return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream));
+  }
+  if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
+  return tapconv_ffma(g, dtype, x, K, ldx, wp, bias, act, y, Nout, ldy, out_nchw_f32, as_stream(stream));
+}
+
+int stcgan_tapwgrad(int geom, int dtype, int backend, const void* S, int N, int SH, int SW, int D0, int lds,
+                    const void* L, int LH, int LW, int D1, int ldl, float* G, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && S && L && G);
+  STCGAN_REQUIRE(geom == STCGAN_GEOM_WIN_S2 || geom == STCGAN_GEOM_WIN_S1);
+  STCGAN_REQUIRE(N >= 0 && SH > 0 && SW > 0 && LH > 0 && LW > 0 && D0 > 0 && D1 > 0 && lds >= D0 && ldl >= D1);
+  if (N == 0) return 0;
+  if (backend == STCGAN_BACKEND_TC) {
+    if (dtype != STCGAN_BF16) return STCGAN_EUNSUPPORTED;
+    return tapwgrad_tc(geom, S, N, SH, SW, D0, lds, L, LH, LW, D1, ldl, G, as_stream(stream));
+  }
+  if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
+  return tapwgrad_ffma(geom, dtype, S, N, SH, SW, D0, lds, L, LH, LW, D1, ldl, G, as_stream(stream));
+}
+
+int stcgan_pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && w && (p1 || p2));
+  return pack_weight(dtype, w, D0, D1, p1, p2, as_stream(stream));
+}
+
+int stcgan_unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, void* stream) {
+  STCGAN_REQUIRE(g && grad);
+  return unpack_grad(g, D0, D1, grad, accumulate, as_stream(stream));
+}
+
+int stcgan_bn_stats(int dtype, const void* y, int64_t P, int C, int ld, double* acc, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && acc && P >= 0 && C > 0 && ld >= C);
+  return bn_stats(dtype, y, P, C, ld, acc, as_stream(stream));
+}
+
+int stcgan_bn_finalize(const double* acc, int64_t P, int C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int training,
+                       float* mean_invstd, float* scale_shift, void* stream) {
+  STCGAN_REQUIRE(C > 0 && gamma && beta && mean_invstd && scale_shift && (acc || !training) && (P > 0 || !training));
+  return bn_finalize(acc, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, mean_invstd,
+                     scale_shift, as_stream(stream));
+}
+
+int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
+                        int HC, int WC, void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && N >= 0 && H > 0 && W > 0 && HC > 0 && WC > 0);
+  return bn_act_apply(dtype, y, N, H, W, C, ldy, scale_shift, HC, WC, out1, ld1, act1, out2, ld2, act2, as_stream(stream));
+}
+
+int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
+                             const float* mean_invstd, int HC, int WC, const void* g1, int ldg1, int act1,
+                             const void* g2, int ldg2, int act2, double* acc, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && acc && HC <= H && WC <= W);
+  return bn_act_bwd_reduce(dtype, y, N, H, W, C, ldy, scale_shift, mean_invstd, HC, WC, g1, ldg1, act1, g2, ldg2, act2,
+                           acc, as_stream(stream));
+}
+
+int stcgan_bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
+                            const float* mean_invstd, const float* gamma, int training, int HC, int WC,
+                            const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
+                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && HC <= H && WC <= W);
+  return bn_act_bwd_apply(dtype, y, N, H, W, C, ldy, scale_shift, mean_invstd, gamma, training, HC, WC, g1, ldg1, act1,
+                          g2, ldg2, act2, acc, dy, lddy, dgamma, dbeta, as_stream(stream));
+}
+
+int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && g && out && P >= 0 && C > 0 && ld >= C);
+  return colsum(dtype, g, P, C, ld, out, as_stream(stream));
+}
+
+int stcgan_pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
+                      int N, int H, int W, void* out, int Cpad, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && out && (c0 == 0 || s0) && (c1 == 0 || s1) && (c2 == 0 || s2));
+  return pack_input(dtype, s0, c0, s1, c1, s2, c2, N, H, W, out, Cpad, as_stream(stream));
+}
+
+int stcgan_unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn,
+                             float* grad_nchw, int accumulate, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && g && grad_nchw && coff >= 0 && cn >= 0 && coff + cn <= ldg);
+  return unpack_input_grad(dtype, g, N, H, W, ldg, coff, cn, grad_nchw, accumulate, as_stream(stream));
+}
+
+int stcgan_nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, float* out, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && x && out && ld >= C);
+  return nhwc_to_nchw(dtype, x, N, H, W, C, ld, out, as_stream(stream));
+}
+
+int stcgan_nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && x && out && ld >= C);
+  return nchw_to_nhwc(dtype, x, N, H, W, C, out, ld, as_stream(stream));
+}
+
+int stcgan_out_act_bwd(int dtype, int act, const float* out_nchw, const float* dout_nchw, int N, int H, int W, int C,
+                       void* g, int ldg, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && out_nchw && dout_nchw && g && ldg >= C);
+  return out_act_bwd(dtype, act, out_nchw, dout_nchw, N, H, W, C, g, ldg, as_stream(stream));
+}
+
+int stcgan_fused_loss(const stcgan_loss_term* host_terms, int nterms, float* loss_out, void* stream) {
+  STCGAN_REQUIRE(host_terms && loss_out);
+  return fused_loss(host_terms, nterms, loss_out, as_stream(stream));
+}
+
+int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blocks, int nblocks,
+                     float* dev_hyper, void* stream) {
+  STCGAN_REQUIRE(dev_table && dev_blocks && dev_hyper);
+  return adam_step(dev_table, dev_blocks, nblocks, dev_hyper, as_stream(stream));
+}
+
+int stcgan_adam_chunk(void) { return 256 * 16; }
+
+int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream) {
+  STCGAN_REQUIRE(nchw && out_nhwc);
+  return float2uint_hwc(nchw, N, C, H, W, out_nhwc, as_stream(stream));
+}
+
+int stcgan_float2uint(const float* in, int64_t n, uint8_t* out, void* stream) {
+  STCGAN_REQUIRE(in && out && n >= 0);
+  return float2uint(in, n, out, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+// BatchNorm2d statistics / apply / backward with the neighbouring LeakyReLU / ReLU fused in,
+// on NHWC tensors.  All kernels are HBM-bound streaming passes with 128-bit accesses
+// (8 bf16 or 4 fp32 channels per thread-load); statistics accumulate in fp64.
+//
+// Reference arithmetic: nn.BatchNorm2d (eps 1e-5, momentum 0.1, affine) + nn.LeakyReLU(0.2, True) /
+// nn.ReLU(True) -- src/models/stcgan_g.py:87-90, src/models/stcgan_d.py:24,36-37,45-46.
+#include "common.cuh"
+
+namespace stcgan {
+
+constexpr int VEC = 8;   // channels per thread (16 B of bf16, 2 x 16 B of fp32)
+
+template <typename T> struct Vec8 { };
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// thread layout shared by all passes: CV = C/8 channel-vectors along x, pixels along y
+struct RowMap {
+  int cv, rows;   // threads per pixel row, pixel rows per block
+};
+static inline RowMap row_map(int C) {
+  RowMap m; m.cv = C / VEC; if (m.cv > 256) m.cv = 256;
+  m.rows = 256 / m.cv; if (m.rows < 1) m.rows = 1;
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics: acc[0][c] += sum y, acc[1][c] += sum y^2     (also used for bias grads via colsum)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ y, long long P, int C, int ld, double* __restrict__ acc,
+                int cv, int rows, int want_sq) {
+  extern __shared__ float red[];   // [rows][cv*8] x2
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  const bool active = tr < rows;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    // one channel-vector column per outer iteration (C > 2048 only)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    if (active) {
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
+        Vec8<T> v; v.load(y + p * ld + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; q[i] = fmaf(v.v[i], v.v[i], q[i]); }
+      }
+    }
+    float* rs = red; float* rq = red + rows * cv * VEC;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rs[(tr * cv + tc) * VEC + i] = s[i]; rq[(tr * cv + tc) * VEC + i] = q[i]; }
+    }
+    __syncthreads();
+    // first cv*8 threads (or loop) reduce over rows in double
+    for (int j = threadIdx.x; j < cv * VEC; j += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      for (int r = 0; r < rows; ++r) { ds += rs[r * cv * VEC + j]; dq += rq[r * cv * VEC + j]; }
+      const int c = (c0 - tc * VEC) + j;
+      atomicAdd(&acc[c], ds);
+      if (want_sq) atomicAdd(&acc[C + c], dq);
+    }
+    __syncthreads();
+  }
+}
+
+// column sums for any channel count (bias gradients: C = 1, 3 or 64): channels along x, pixels along y
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ g, long long P, int C, int ld, float* __restrict__ out, int cc, int rows) {
+  __shared__ float red[256];
+  const int tc = threadIdx.x % cc, tr = threadIdx.x / cc;
+  for (int c0 = 0; c0 < C; c0 += cc) {
+    const int c = c0 + tc;
+    float s = 0.f;
+    if (tr < rows && c < C)
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows)
+        s += to_f32<T>(g[p * ld + c]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (tr == 0 && c < C) {
+      float t = 0.f;
+      for (int r = 0; r < rows; ++r) t += red[r * cc + tc];
+      atomicAdd(&out[c], t);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ acc, long long P, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
+                                   int training, float* __restrict__ mean_invstd, float* __restrict__ scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    const double m = acc[c] / (double)P;
+    double var = acc[C + c] / (double)P - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+      const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rmean[c];
+    invstd = 1.f / sqrtf(rvar[c] + eps);
+  }
+  mean_invstd[c] = mean; mean_invstd[C + c] = invstd;
+  const float sc = gamma[c] * invstd;
+  scale_shift[c] = sc; scale_shift[C + c] = beta[c] - mean * sc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward apply (+ activation, optional second output with another activation, optional crop)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const float* __restrict__ ss,
+                    int HC, int WC, long long PC, T* __restrict__ o1, int ld1, int act1,
+                    T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  if (tr >= rows) return;
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = ss ? ss[c0 + i] : 1.f; sh[i] = ss ? ss[C + c0 + i] : 0.f; }
+    for (long long p = (long long)blockIdx.x * rows + tr; p < PC; p += (long long)gridDim.x * rows) {
+      const int w = (int)(p % WC); const long long t = p / WC;
+      const int h = (int)(t % HC); const long long n = t / HC;
+      Vec8<T> v; v.load(y + ((n * H + h) * W + w) * (long long)ldy + c0);
+      Vec8<T> a, b;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(v.v[i], sc[i], sh[i]);
+        a.v[i] = act_fwd(act1, z);
+        b.v[i] = act_fwd(act2, z);
+      }
+      a.store(o1 + p * ld1 + c0);
+      if (o2) b.store(o2 + p * ld2 + c0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load_dz(const T* y, int H, int W, int ldy, const float* sc, const float* sh,
+                                        const float* mean, const float* invstd, bool has_bn,
+                                        int HC, int WC, const T* g1, int ldg1, int act1,
+                                        const T* g2, int ldg2, int act2,
+                                        long long p, int c0, float* dz, float* xhat) {
+  // p indexes the FULL [N,H,W] grid
+  const int w = (int)(p % W); const long long t = p / W;
+  const int h = (int)(t % H); const long long n = t / H;
+  Vec8<T> v; v.load(y + p * ldy + c0);
+  const bool inside = h < HC && w < WC;
+  Vec8<T> a, b;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a.v[i] = 0.f; b.v[i] = 0.f; }
+  if (inside) {
+    const long long pc = (n * HC + h) * WC + w;
+    a.load(g1 + pc * ldg1 + c0);
+    if (g2) b.load(g2 + pc * ldg2 + c0);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float z = has_bn ? fmaf(v.v[i], sc[i], sh[i]) : v.v[i];
+    dz[i] = a.v[i] * act_gate(act1, z) + (g2 ? b.v[i] * act_gate(act2, z) : 0.f);
+    xhat[i] = has_bn ? (v.v[i] - mean[i]) * invstd[i] : 0.f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
+                     const float* __restrict__ ss, const float* __restrict__ mi, int HC, int WC,
+                     const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
+                     double* __restrict__ acc, int cv, int rows) {
+  extern __shared__ float red[];
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  const bool active = tr < rows;
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8], mean[8], invstd[8], s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; invstd[i] = mi[C + c0 + i];
+      s[i] = 0.f; q[i] = 0.f;
+    }
+    if (active) {
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
+        float dz[8], xh[8];
+        load_dz<T>(y, H, W, ldy, sc, sh, mean, invstd, true, HC, WC, g1, ldg1, act1, g2, ldg2, act2, p, c0, dz, xh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], xh[i], q[i]); }
+      }
+    }
+    float* rs = red; float* rq = red + rows * cv * VEC;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rs[(tr * cv + tc) * VEC + i] = s[i]; rq[(tr * cv + tc) * VEC + i] = q[i]; }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cv * VEC; j += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      for (int r = 0; r < rows; ++r) { ds += rs[r * cv * VEC + j]; dq += rq[r * cv * VEC + j]; }
+      const int c = (c0 - tc * VEC) + j;
+      atomicAdd(&acc[c], ds);
+      atomicAdd(&acc[C + c], dq);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
+                    const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ gamma,
+                    int training, int HC, int WC,
+                    const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
+                    const double* __restrict__ acc, T* __restrict__ dy, int lddy,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int cv, int rows) {
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  const bool has_bn = ss != nullptr;
+  if (has_bn && blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dgamma[c] += (float)acc[C + c];
+      dbeta[c] += (float)acc[c];
+    }
+  }
+  if (tr >= rows) return;
+  const float invP = 1.f / (float)P;
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8], mean[8], invstd[8], k0[8], k1[8], k2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (has_bn) {
+        sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; invstd[i] = mi[C + c0 + i];
+        const float gi = gamma[c0 + i] * invstd[i];
+        k0[i] = gi;
+        k1[i] = training ? gi * (float)(acc[c0 + i]) * invP : 0.f;       // gamma*invstd*mean(dz)
+        k2[i] = training ? gi * (float)(acc[C + c0 + i]) * invP : 0.f;   // gamma*invstd*mean(dz*xhat)
+      } else {
+        sc[i] = 1.f; sh[i] = 0.f; mean[i] = 0.f; invstd[i] = 1.f; k0[i] = 1.f; k1[i] = 0.f; k2[i] = 0.f;
+      }
+    }
+    for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
+      float dz[8], xh[8];
+      load_dz<T>(y, H, W, ldy, sc, sh, mean, invstd, has_bn, HC, WC, g1, ldg1, act1, g2, ldg2, act2, p, c0, dz, xh);
+      Vec8<T> o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = k0[i] * dz[i] - k1[i] - xh[i] * k2[i];
+      o.store(dy + p * lddy + c0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline unsigned stream_grid(long long P, int rows) {
+  long long b = (P + rows - 1) / rows;
+  const long long cap = 148LL * 8;   // 8 resident 256-thread CTAs per SM, one wave
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+static int bn_stats_t(const void* y, long long P, int C, int ld, double* acc, int want_sq, cudaStream_t st) {
+  const RowMap m = row_map(C);
+  const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
+  bn_stats_kernel<T><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(static_cast<const T*>(y), P, C, ld, acc, m.cv, m.rows, want_sq);
+  return finish_launch();
+}
+
+int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st) {
+  const int esz = dtype == STCGAN_F32 ? 4 : 2;
+  if (C % VEC != 0 || C > 2048 || !aligned16(y) || ((long long)ld * esz) % 16 != 0) return STCGAN_EINVAL;
+  if (P == 0) return 0;
+  return dtype == STCGAN_F32 ? bn_stats_t<float>(y, P, C, ld, acc, 1, st) : bn_stats_t<__nv_bfloat16>(y, P, C, ld, acc, 1, st);
+}
+
+int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
+                float momentum, float eps, int training, float* mean_invstd, float* scale_shift, cudaStream_t st) {
+  if (!training && (!rmean || !rvar)) return STCGAN_EINVAL;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, P, C, gamma, beta, rmean, rvar, momentum, eps, training,
+                                                      mean_invstd, scale_shift);
+  return finish_launch();
+}
+
+static bool vec_ok(int dtype, const void* p, int ld) {
+  const int esz = dtype == STCGAN_F32 ? 4 : 2;
+  return p == nullptr || (aligned16(p) && ((long long)ld * esz) % 16 == 0);
+}
+
+int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, int HC, int WC,
+                 void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st) {
+  if (C % VEC != 0 || C > 2048 || HC > H || WC > W || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, o1, ld1) || !vec_ok(dtype, o2, ld2) || !o1)
+    return STCGAN_EINVAL;
+  const long long PC = (long long)N * HC * WC;
+  if (PC == 0) return 0;
+  const RowMap m = row_map(C);
+  if (dtype == STCGAN_F32)
+    bn_act_apply_kernel<float><<<stream_grid(PC, m.rows * 2), 256, 0, st>>>(
+        static_cast<const float*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
+        static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
+  else
+    bn_act_apply_kernel<__nv_bfloat16><<<stream_grid(PC, m.rows * 2), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
+        static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
+  return finish_launch();
+}
+
+int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                      int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
+                      double* acc, cudaStream_t st) {
+  if (C % VEC != 0 || C > 2048 || !ss || !mi || !g1 || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2))
+    return STCGAN_EINVAL;
+  const long long P = (long long)N * H * W;
+  if (P == 0) return 0;
+  const RowMap m = row_map(C);
+  const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
+  if (dtype == STCGAN_F32)
+    bn_bwd_reduce_kernel<float><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(
+        static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
+        static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
+        act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
+  return finish_launch();
+}
+
+int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                     const float* gamma, int training, int HC, int WC, const void* g1, int ldg1, int act1,
+                     const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
+                     float* dgamma, float* dbeta, cudaStream_t st) {
+  if (C % VEC != 0 || C > 2048 || !g1 || !dy || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2) ||
+      !vec_ok(dtype, dy, lddy))
+    return STCGAN_EINVAL;
+  if (ss && (!mi || !gamma || (training && !acc))) return STCGAN_EINVAL;
+  const long long P = (long long)N * H * W;
+  if (P == 0) return 0;
+  const RowMap m = row_map(C);
+  if (dtype == STCGAN_F32)
+    bn_bwd_apply_kernel<float><<<stream_grid(P, m.rows * 2), 256, 0, st>>>(
+        static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
+        act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 2), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
+        static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
+        static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
+  return finish_launch();
+}
+
+int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cudaStream_t st) {
+  if (P == 0 || C == 0) return 0;
+  const int cc = C < 256 ? C : 256, rows = 256 / cc;
+  long long b = (P + rows * 8 - 1) / (rows * 8); if (b > 148 * 8) b = 148 * 8; if (b < 1) b = 1;
+  if (dtype == STCGAN_F32)
+    colsum_kernel<float><<<(unsigned)b, 256, 0, st>>>(static_cast<const float*>(g), P, C, ld, out, cc, rows);
+  else
+    colsum_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), P, C, ld, out, cc, rows);
+  return finish_launch();
+}
+
+}  // namespace stcgan

@@ -1,0 +1,417 @@
+// Layout, loss, optimiser and quantisation kernels (all HBM-/latency-bound streaming work).
+#include "common.cuh"
+
+namespace stcgan {
+
+// ---------------------------------------------------------------------------------------------
+// weight pack: W[d0][d1][16] fp32 -> P1[t][d0][d1], P2[t][d1][d0]  (T)
+// one block = 16 d0 x 32 d1 tile, all 16 taps; smem transposes so that every global access is coalesced
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, int D0, int D1, T* __restrict__ p1, T* __restrict__ p2) {
+  __shared__ float tile[16][32 * 16 + 1];   // [d0][d1*16 + t]
+  const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 32;
+  // load: rows of 32*16 contiguous floats per d0
+  for (int i = threadIdx.x; i < 16 * 512; i += 256) {
+    const int r = i / 512, c = i % 512;
+    const int d0 = a0 + r, d1 = b0 + c / 16;
+    tile[r][c] = (d0 < D0 && d1 < D1) ? w[((long long)d0 * D1 + b0) * 16 + c] : 0.f;
+  }
+  __syncthreads();
+  if (p1) {
+    for (int i = threadIdx.x; i < 16 * 16 * 32; i += 256) {
+      const int t = i / 512, r = (i / 32) % 16, c = i % 32;   // consecutive threads -> consecutive d1
+      const int d0 = a0 + r, d1 = b0 + c;
+      if (d0 < D0 && d1 < D1) p1[((long long)t * D0 + d0) * D1 + d1] = from_f32<T>(tile[r][c * 16 + t]);
+    }
+  }
+  if (p2) {
+    for (int i = threadIdx.x; i < 16 * 16 * 32; i += 256) {
+      const int t = i / 512, c = (i / 16) % 32, r = i % 16;   // consecutive threads -> consecutive d0
+      const int d0 = a0 + r, d1 = b0 + c;
+      if (d0 < D0 && d1 < D1) p2[((long long)t * D1 + d1) * D0 + d0] = from_f32<T>(tile[r][c * 16 + t]);
+    }
+  }
+}
+
+int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, cudaStream_t st) {
+  if (D0 <= 0 || D1 <= 0) return STCGAN_EINVAL;
+  dim3 grid((D1 + 31) / 32, (D0 + 15) / 16);
+  if (dtype == STCGAN_F32)
+    pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, D0, D1, static_cast<float*>(p1), static_cast<float*>(p2));
+  else
+    pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, D0, D1, static_cast<__nv_bfloat16*>(p1),
+                                                            static_cast<__nv_bfloat16*>(p2));
+  return finish_launch();
+}
+
+// G[t][d0][d1] -> grad[d0][d1][16]
+__global__ void __launch_bounds__(256)
+unpack_grad_kernel(const float* __restrict__ g, int D0, int D1, float* __restrict__ grad, int accumulate) {
+  __shared__ float tile[16][32 * 8 + 1];   // [t][d0_local*32 + d1_local], 8 d0 x 32 d1 per block
+  const int a0 = blockIdx.y * 8, b0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 16 * 256; i += 256) {
+    const int t = i / 256, r = (i / 32) % 8, c = i % 32;
+    const int d0 = a0 + r, d1 = b0 + c;
+    tile[t][r * 32 + c] = (d0 < D0 && d1 < D1) ? g[((long long)t * D0 + d0) * D1 + d1] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * 512; i += 256) {
+    const int r = i / 512, c = (i % 512) / 16, t = i % 16;
+    const int d0 = a0 + r, d1 = b0 + c;
+    if (d0 < D0 && d1 < D1) {
+      float* dst = &grad[((long long)d0 * D1 + d1) * 16 + t];
+      const float v = tile[t][r * 32 + c];
+      *dst = accumulate ? *dst + v : v;
+    }
+  }
+}
+
+int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cudaStream_t st) {
+  if (D0 <= 0 || D1 <= 0) return STCGAN_EINVAL;
+  dim3 grid((D1 + 31) / 32, (D0 + 7) / 8);
+  unpack_grad_kernel<<<grid, 256, 0, st>>>(g, D0, D1, grad, accumulate);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// module-boundary layouts
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
+                  const float* __restrict__ s2, int c2, int N, long long HW, T* __restrict__ out, int Cpad) {
+  const long long P = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, r = p % HW;
+    T* o = out + p * Cpad;
+    int c = 0;
+    for (int i = 0; i < c0; ++i) o[c++] = from_f32<T>(s0[(n * c0 + i) * HW + r]);
+    for (int i = 0; i < c1; ++i) o[c++] = from_f32<T>(s1[(n * c1 + i) * HW + r]);
+    for (int i = 0; i < c2; ++i) o[c++] = from_f32<T>(s2[(n * c2 + i) * HW + r]);
+    for (; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
+  }
+}
+
+int pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
+               int N, int H, int W, void* out, int Cpad, cudaStream_t st) {
+  if (c0 + c1 + c2 > Cpad || c0 < 0 || c1 < 0 || c2 < 0) return STCGAN_EINVAL;
+  const long long HW = (long long)H * W, P = N * HW;
+  if (P == 0) return 0;
+  long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  if (dtype == STCGAN_F32)
+    pack_input_kernel<float><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, HW, static_cast<float*>(out), Cpad);
+  else
+    pack_input_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, HW,
+                                                                  static_cast<__nv_bfloat16*>(out), Cpad);
+  return finish_launch();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpack_input_grad_kernel(const T* __restrict__ g, int N, long long HW, int ldg, int coff, int cn,
+                         float* __restrict__ grad, int accumulate) {
+  const long long P = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, r = p % HW;
+    for (int c = 0; c < cn; ++c) {
+      float* dst = &grad[(n * cn + c) * HW + r];
+      const float v = to_f32<T>(g[p * ldg + coff + c]);
+      *dst = accumulate ? *dst + v : v;
+    }
+  }
+}
+
+int unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn, float* grad,
+                      int accumulate, cudaStream_t st) {
+  const long long HW = (long long)H * W, P = N * HW;
+  if (P == 0 || cn == 0) return 0;
+  long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  if (dtype == STCGAN_F32)
+    unpack_input_grad_kernel<float><<<(unsigned)b, 256, 0, st>>>(static_cast<const float*>(g), N, HW, ldg, coff, cn, grad, accumulate);
+  else
+    unpack_input_grad_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, HW, ldg,
+                                                                         coff, cn, grad, accumulate);
+  return finish_launch();
+}
+
+// generic NHWC <-> NCHW through a 32x32 smem transpose over (pixel, channel)
+template <typename T, bool TO_NCHW>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const void* __restrict__ src, void* __restrict__ dst, long long HW, int C, int ld) {
+  __shared__ float tile[32][33];
+  const long long n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32; const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;   // 32 x 8
+  if (TO_NCHW) {
+    const T* x = static_cast<const T*>(src); float* o = static_cast<float*>(dst);
+    for (int j = ty; j < 32; j += 8) {   // rows = pixels, tx = channel (contiguous in NHWC)
+      const long long p = p0 + j; const int c = c0 + tx;
+      tile[j][tx] = (p < HW && c < C) ? to_f32<T>(x[(n * HW + p) * ld + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {   // rows = channels, tx = pixel (contiguous in NCHW)
+      const int c = c0 + j; const long long p = p0 + tx;
+      if (c < C && p < HW) o[(n * C + c) * HW + p] = tile[tx][j];
+    }
+  } else {
+    const float* x = static_cast<const float*>(src); T* o = static_cast<T*>(dst);
+    for (int j = ty; j < 32; j += 8) {
+      const int c = c0 + j; const long long p = p0 + tx;
+      tile[j][tx] = (c < C && p < HW) ? x[(n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      const long long p = p0 + j; const int c = c0 + tx;
+      if (p < HW && c < C) o[(n * HW + p) * ld + c] = from_f32<T>(tile[tx][j]);
+    }
+  }
+}
+
+int nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, float* out, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  if (N == 0 || HW == 0 || C == 0) return 0;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+  if (dtype == STCGAN_F32) transpose_kernel<float, true><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  else transpose_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  return finish_launch();
+}
+
+int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  if (N == 0 || HW == 0 || C == 0) return 0;
+  dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+  if (dtype == STCGAN_F32) transpose_kernel<float, false><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  else transpose_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  return finish_launch();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+out_act_bwd_kernel(int act, const float* __restrict__ o, const float* __restrict__ d, int N, long long HW, int C,
+                   T* __restrict__ g, int ldg) {
+  const long long P = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, r = p % HW;
+    for (int c = 0; c < C; ++c) {
+      const float ov = o[(n * C + c) * HW + r], dv = d[(n * C + c) * HW + r];
+      const float gv = act == STCGAN_ACT_TANH ? dv * (1.f - ov * ov)
+                     : act == STCGAN_ACT_SIGMOID ? dv * ov * (1.f - ov) : dv;
+      g[p * ldg + c] = from_f32<T>(gv);
+    }
+  }
+}
+
+int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, void* g, int ldg,
+                cudaStream_t st) {
+  const long long HW = (long long)H * W, P = N * HW;
+  if (P == 0) return 0;
+  long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  if (dtype == STCGAN_F32) out_act_bwd_kernel<float><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, HW, C, static_cast<float*>(g), ldg);
+  else out_act_bwd_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, HW, C, static_cast<__nv_bfloat16*>(g), ldg);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused losses: value + gradient for up to 8 terms in one launch
+// ---------------------------------------------------------------------------------------------
+struct LossTerms { stcgan_loss_term t[8]; int n; long long first_block[9]; };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int LOSS_ELEMS_PER_BLOCK = 256 * 8;
+
+__global__ void __launch_bounds__(256)
+fused_loss_kernel(const LossTerms lt, float* __restrict__ loss_out) {
+  __shared__ float red[8];
+  int ti = 0;
+  while (ti + 1 < lt.n && (long long)blockIdx.x >= lt.first_block[ti + 1]) ++ti;
+  const stcgan_loss_term t = lt.t[ti];
+  const long long base = ((long long)blockIdx.x - lt.first_block[ti]) * LOSS_ELEMS_PER_BLOCK;
+  const float inv_n = 1.f / (float)t.n;
+  const float gw = t.weight * inv_n;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long i = base + j * 256 + threadIdx.x;
+    if (i >= t.n) continue;
+    const float a = t.a[i];
+    float term, grad;
+    if (t.kind == 0) {                 // L1 (F.l1_loss: sign(a-b), 0 at equality)
+      const float d = a - t.b[i];
+      term = fabsf(d);
+      grad = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else if (t.kind == 1) {          // MSE against a scalar label
+      const float d = a - t.target;
+      term = d * d;
+      grad = 2.f * d;
+    } else {                           // BCE with logits: max(a,0) - a*y + log1p(exp(-|a|))
+      term = fmaxf(a, 0.f) - a * t.target + log1pf(expf(-fabsf(a)));
+      grad = 1.f / (1.f + expf(-a)) - t.target;
+    }
+    s += term;
+    if (t.grad) {
+      const float gv = gw * grad;
+      t.grad[i] = t.accumulate ? t.grad[i] + gv : gv;
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(&loss_out[t.slot], v * t.loss_weight * inv_n);
+  }
+}
+
+int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st) {
+  if (nterms < 1 || nterms > 8) return STCGAN_EINVAL;
+  LossTerms lt; lt.n = nterms;
+  long long nb = 0;
+  for (int i = 0; i < nterms; ++i) {
+    if (terms[i].n <= 0 || terms[i].kind < 0 || terms[i].kind > 2 || !terms[i].a) return STCGAN_EINVAL;
+    if (terms[i].kind == 0 && !terms[i].b) return STCGAN_EINVAL;
+    lt.t[i] = terms[i];
+    lt.first_block[i] = nb;
+    nb += (terms[i].n + LOSS_ELEMS_PER_BLOCK - 1) / LOSS_ELEMS_PER_BLOCK;
+  }
+  lt.first_block[nterms] = nb;
+  fused_loss_kernel<<<(unsigned)nb, 256, 0, st>>>(lt, loss_out);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-tensor Adam (torch.optim.Adam semantics: eps added after sqrt(v_hat); no weight decay / amsgrad)
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ---------------------------------------------------------------------------------------------
+constexpr int ADAM_CHUNK = 256 * 16;   // elements per block
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,
+                                            float step_size, float inv_bc2_sqrt) {
+  m = beta1 * m + (1.f - beta1) * g;
+  v = beta2 * v + (1.f - beta2) * g * g;
+  const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restrict__ blocks,
+            const float* __restrict__ hyper) {
+  const float step_size = hyper[6], inv_bc2_sqrt = hyper[7], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3],
+              grad_scale = hyper[4];
+  const int ti = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
+  const stcgan_adam_tensor t = table[ti];
+  const long long base = (long long)chunk * ADAM_CHUNK;
+  if (t.d0 > 0) {
+    // packed gradients G[tap][d0][d1]: one thread owns one (d0,d1) pair = 16 contiguous parameters (64 B);
+    // its 16 gradient reads are coalesced across the warp (consecutive pairs of one tap plane).
+    const long long plane = (long long)t.d0 * t.d1;
+    const long long r = base / 16 + threadIdx.x;
+    if (r >= plane) return;
+    float* pp = t.p + r * 16; float* pm = t.m + r * 16; float* pv = t.v + r * 16;
+    const bool vec = ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv)) & 15) == 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float p[4], m[4], v[4];
+      if (vec) {
+        const float4 a = *reinterpret_cast<const float4*>(pp + 4 * q), b = *reinterpret_cast<const float4*>(pm + 4 * q),
+                     c = *reinterpret_cast<const float4*>(pv + 4 * q);
+        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; m[0] = b.x; m[1] = b.y; m[2] = b.z; m[3] = b.w;
+        v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { p[k] = pp[4 * q + k]; m[k] = pm[4 * q + k]; v[k] = pv[4 * q + k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g = t.g[(long long)(4 * q + k) * plane + r] * grad_scale;
+        adam_update(p[k], m[k], v[k], g, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(pm + 4 * q) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(pv + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { pp[4 * q + k] = p[k]; pm[4 * q + k] = m[k]; pv[4 * q + k] = v[k]; }
+      }
+    }
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+      const long long i = base + j * 256 + threadIdx.x;
+      if (i >= t.n) continue;
+      float p = t.p[i], m = t.m[i], v = t.v[i];
+      adam_update(p, m, v, t.g[i] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+      t.p[i] = p; t.m[i] = m; t.v[i] = v;
+    }
+  }
+}
+
+// steps_done += 1; bias corrections in double like torch (1 - beta^t)
+__global__ void adam_tick_kernel(float* __restrict__ hyper) {
+  const float step = hyper[5] + 1.f;
+  hyper[5] = step;
+  const double bc1 = 1.0 - pow((double)hyper[1], (double)step);
+  const double bc2 = 1.0 - pow((double)hyper[2], (double)step);
+  hyper[6] = (float)((double)hyper[0] / bc1);
+  hyper[7] = (float)(1.0 / sqrt(bc2));
+}
+
+int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st) {
+  if (nblocks <= 0) return STCGAN_EINVAL;
+  adam_tick_kernel<<<1, 1, 0, st>>>(hyper);
+  ++g_launches;
+  adam_kernel<<<nblocks, 256, 0, st>>>(table, blocks, hyper);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// float2uint: numpy semantics  (np.clip(a*0.5+0.5, 0, 1) * 255).astype(uint8), all in fp32
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t f2u(float a) {
+  a = fminf(fmaxf(a, 0.f), 1.f);
+  return (uint8_t)(__fmul_rn(a, 255.f));   // C-style truncation toward zero, like astype(uint8) on [0,255]
+}
+
+__global__ void __launch_bounds__(256)
+float2uint_kernel(const float* __restrict__ in, long long n, uint8_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = f2u(in[i]);
+}
+
+__global__ void __launch_bounds__(256)
+float2uint_hwc_kernel(const float* __restrict__ in, int N, int C, long long HW, uint8_t* __restrict__ out) {
+  const long long P = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, r = p % HW;
+    for (int c = 0; c < C; ++c) {
+      const float v = in[(n * C + c) * HW + r];
+      out[p * C + c] = f2u(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f));   // no FMA contraction: numpy rounds twice
+    }
+  }
+}
+
+int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st) {
+  if (n == 0) return 0;
+  long long b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  float2uint_kernel<<<(unsigned)b, 256, 0, st>>>(in, n, out);
+  return finish_launch();
+}
+
+int float2uint_hwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st) {
+  const long long HW = (long long)H * W, P = N * HW;
+  if (P == 0) return 0;
+  long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  float2uint_hwc_kernel<<<(unsigned)b, 256, 0, st>>>(in, N, C, HW, out);
+  return finish_launch();
+}
+
+}  // namespace stcgan

@@ -1,0 +1,583 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 operands, fp32 accumulate).
+//
+//   forward + dgrad ("tap GEMM"):   out[p, n] = sum_taps sum_k  A_tap[p, k] * Wp[tap][n][k]
+//       A_tap is a TMA box of the NHWC activation tensor, shifted by the tap offset; stride-2 windows are read
+//       through four parity views of the tensor (plain tiled TMA, unit element strides); out-of-range rows,
+//       columns and images are zero-filled by TMA, which implements the conv padding (and the reference's
+//       odd-size F.pad) for free.  Both operands are K-major, 128-byte swizzled.
+//   wgrad:                          G[tap][d0][d1] += sum_p S[p, d0] * L[win_tap(p), d1]
+//       the reduction runs over pixels, which is the slow dimension of NHWC, so both operands are MN-major
+//       (128-byte swizzled rows of 64 channels); split over pixel tiles, fp32 red.global.add into G.
+//
+// One CTA = one 128 x BN accumulator tile in TMEM.  Warp 0: TMA producer (one thread).  Warp 1: TMEM allocator and
+// MMA issuer (one thread issues tcgen05.mma / tcgen05.commit).  Warps 2-5: epilogue (tcgen05.ld 32x32b, bias +
+// activation, 128-bit stores).  smem ring of STAGES x (A tile + B tile) guarded by full/empty mbarriers.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace stcgan {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin on the barrier phase.  A broken pipeline must not hang the GPU: after ~2 s of waiting the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (spin == 1024) t0 = clock64();
+    if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]   (kind::f16 covers bf16 inputs, fp32 accumulation)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptors
+// ---------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, 128-byte swizzle, Blackwell version bit set.
+//   K-major operand  (rows of 64 bf16 = 128 B along K): SBO = 1024 B between 8-row groups, LBO unused (=1)
+//   MN-major operand (rows of 64 bf16 = 128 B along M/N, one row per K index): SBO = 1024 B between 8-K groups,
+//                     LBO = byte distance between consecutive 64-element M/N blocks
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // D format: fp32
+       | (1u << 7) | (1u << 10)          // A, B format: bf16
+       | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
+       | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128, TC_BK = 64;
+
+struct alignas(64) TapGemmParams {
+  CUtensorMap amap[4];     // activation views (view 0 only for unit-stride geometries)
+  CUtensorMap bmap;        // packed weights as a 2D tensor [16*Nout rows][K]
+  // per-class tap tables, already translated to view coordinates
+  int8_t tdy[4][16], tdx[4][16], tview[4][16], twt[4][16];
+  int8_t oy0[4], ox0[4];
+  int ntaps, kchunks;
+  int N, OH, OW, ostride;
+  int GH, GW;              // largest class grid
+  int wt, ht, nt;          // tile box: wt*ht*nt = 128 grid pixels
+  int tiles_w, tiles_h;    // tiles along the grid; blockIdx.x enumerates (n-tile, h-tile, w-tile)
+  int Nout, ldy, act;
+  const float* bias;
+  __nv_bfloat16* y;
+};
+
+template <int BN, int STAGES>
+struct TapGemmSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192)
+tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
+  using SM = TapGemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = blockIdx.z;
+  const int n_col0 = blockIdx.y * BN;
+  const int tw = blockIdx.x % P.tiles_w;
+  const int th = (blockIdx.x / P.tiles_w) % P.tiles_h;
+  const int tn = blockIdx.x / (P.tiles_w * P.tiles_h);
+  const int b0 = tw * P.wt, a0 = th * P.ht, n0 = tn * P.nt;
+  const int iters = P.ntaps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&P.bmap);
+    tma_prefetch_desc(&P.amap[0]);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ===== TMA producer =====
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int j = it / P.kchunks, kc = it % P.kchunks;
+      uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+      uint8_t* b_dst = a_dst + SM::A_BYTES;
+      mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+      tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
+      tma_load_2d(&P.bmap, &full_bar[s], b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0);
+    }
+  } else if (threadIdx.x == 32) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < TC_BK / 16; ++k) {
+        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+        umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+      }
+      umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+    }
+    umma_commit(tmem_full);
+  } else if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> bias/activation -> bf16 NHWC =====
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // accumulator row = grid pixel inside the tile
+    const int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
+    const int a = a0 + hl, b = b0 + wl, n = n0 + nl;
+    const int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
+    const bool valid = n < P.N && oy < P.OH && ox < P.OW;
+    __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (valid) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+            if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
+            f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(out + c0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel: G[tap][d0 tile 128][d1 tile BN] += sum over this CTA's pixel tiles
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) WgradParams {
+  CUtensorMap smap;        // S  [N, SH, SW, D0]
+  CUtensorMap lmap[4];     // L views (parity views for stride 2)
+  int8_t tdy[16], tdx[16], tview[16];
+  int wt, ht, nt;          // pixel tile box: wt*ht*nt = 64
+  int tiles_w, tiles_h, tiles_n;
+  int tiles_per_split;     // pixel tiles handled by one CTA (blockIdx.z = split)
+  int D0, D1;
+  float* G;
+};
+
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int A_BYTES = 128 * 64 * 2;        // two [64 px][64 ch] blocks
+  static constexpr int B_BYTES = BN * 64 * 2;         // BN/64 blocks
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192)
+tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
+  using SM = WgradSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles1 = P.D1 / BN;
+  const int d0_0 = (blockIdx.x / tiles1) * 128, d1_0 = (blockIdx.x % tiles1) * BN;
+  const int tap = blockIdx.y;
+  const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int t_begin = blockIdx.z * P.tiles_per_split;
+  int t_end = t_begin + P.tiles_per_split;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int iters = t_end - t_begin;     // host guarantees >= 1
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&P.smap);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    const CUtensorMap* lm = &P.lmap[P.tview[tap]];
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int t = t_begin + it;
+      const int b0 = (t % P.tiles_w) * P.wt, a0 = ((t / P.tiles_w) % P.tiles_h) * P.ht, n0 = (t / (P.tiles_w * P.tiles_h)) * P.nt;
+      uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+      uint8_t* b_dst = a_dst + SM::A_BYTES;
+      mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+      tma_load_4d(&P.smap, &full_bar[s], a_dst, d0_0, b0, a0, n0);
+      tma_load_4d(&P.smap, &full_bar[s], a_dst + 8192, d0_0 + 64, b0, a0, n0);
+#pragma unroll
+      for (int h = 0; h < BN / 64; ++h)
+        tma_load_4d(lm, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0 + P.tdx[tap], a0 + P.tdy[tap], n0);
+    }
+  } else if (threadIdx.x == 32) {
+    constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);     // both operands MN-major
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {   // 64 pixels per stage = 4 x K16; 16 K-rows = 2048 B
+        const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);
+        const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);
+        umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+      }
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(tmem_full);
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int d0 = d0_0 + q * 32 + lane;
+    float* out = P.G + ((long long)tap * P.D0 + d0) * P.D1 + d1_0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) atomicAdd(out + c0 + e, __uint_as_float(r[e]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 tensor view: dims (C, W, H, N) with element strides (1, sw, sh, sn); box (64, bw, bh, bn); 128B swizzle
+static int encode_nhwc(CUtensorMap* m, const void* base, long long C, long long W, long long H, long long N,
+                       long long sw, long long sh, long long sn, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  if (W < 1) W = 1;
+  if (H < 1) H = 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+static int encode_2d(CUtensorMap* m, const void* base, long long K, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// choose a box (wt, ht, nt) of `total` grid pixels (powers of two) that wastes the fewest MMA rows
+static void choose_tile(int total, int GW, int GH, int N, int* wt, int* ht, int* nt) {
+  double best = -1.0;
+  for (int w = 1; w <= total; w *= 2)
+    for (int h = 1; w * h <= total; h *= 2) {
+      const int n = total / (w * h);
+      const long long tiles = (long long)((GW + w - 1) / w) * ((GH + h - 1) / h) * ((N + n - 1) / n);
+      const double util = (double)GW * GH * N / ((double)tiles * total);
+      // prefer wide boxes on ties (longer contiguous runs for TMA)
+      const double score = util + 1e-6 * w + 1e-9 * h;
+      if (score > best) { best = score; *wt = w; *ht = h; *nt = n; }
+    }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, int STAGES>
+static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
+  using SM = TapGemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  tapgemm_tc_kernel<BN, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  return finish_launch();
+}
+
+int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
+               void* y, int Nout, int ldy, cudaStream_t st) {
+  if (K % 64 != 0 || Nout % 64 != 0 || ldx % 8 != 0 || ldy % 8 != 0 || !al16(x) || !al16(y) || !al16(wp))
+    return STCGAN_EUNSUPPORTED;
+  if (act == STCGAN_ACT_TANH || act == STCGAN_ACT_SIGMOID) return STCGAN_EUNSUPPORTED;
+  TapGemmParams P;
+  memset(&P, 0, sizeof(P));
+  int GH = 0, GW = 0;
+  for (int c = 0; c < g.nclass; ++c) {
+    if (g.grid_h(c) > GH) GH = g.grid_h(c);
+    if (g.grid_w(c) > GW) GW = g.grid_w(c);
+    P.oy0[c] = g.oy0[c]; P.ox0[c] = g.ox0[c];
+  }
+  if (GH <= 0 || GW <= 0) return 0;
+  choose_tile(TC_BM, GW, GH, g.N, &P.wt, &P.ht, &P.nt);
+  P.tiles_w = (GW + P.wt - 1) / P.wt; P.tiles_h = (GH + P.ht - 1) / P.ht;
+  const int tiles_n = (g.N + P.nt - 1) / P.nt;
+  P.GH = GH; P.GW = GW; P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.ostride = g.ostride;
+  P.ntaps = g.ntaps; P.kchunks = K / 64;
+  P.Nout = Nout; P.ldy = ldy; P.act = act; P.bias = bias; P.y = static_cast<__nv_bfloat16*>(y);
+
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const long long sn = (long long)g.IH * g.IW * ldx;
+  int rc;
+  if (g.istride == 1) {
+    rc = encode_nhwc(&P.amap[0], xb, K, g.IW, g.IH, g.N, ldx, (long long)g.IW * ldx, sn, P.wt, P.ht, P.nt);
+    if (rc) return rc;
+    for (int v = 1; v < 4; ++v) P.amap[v] = P.amap[0];
+  } else {
+    for (int p = 0; p < 2; ++p)
+      for (int q = 0; q < 2; ++q) {
+        const long long vw = (g.IW - q + 1) / 2, vh = (g.IH - p + 1) / 2;   // rows 2a'+p < IH
+        // a view can be empty when IH or IW == 1; keep a valid 1-wide map (never selected inside range)
+        rc = encode_nhwc(&P.amap[p * 2 + q], xb + ((long long)p * g.IW + q) * ldx, K, vw, vh, g.N,
+                         2LL * ldx, 2LL * g.IW * ldx, sn, P.wt, P.ht, P.nt);
+        if (rc) return rc;
+      }
+  }
+  rc = encode_2d(&P.bmap, wp, K, 16LL * Nout, Nout % 128 == 0 ? 128 : 64);
+  if (rc) return rc;
+
+  for (int c = 0; c < g.nclass; ++c)
+    for (int j = 0; j < g.ntaps; ++j) {
+      const Tap& t = g.tap[c][j];
+      if (g.istride == 2) {
+        const int p = t.dy & 1, q = t.dx & 1;
+        P.tview[c][j] = (int8_t)(p * 2 + q);
+        P.tdy[c][j] = (int8_t)((t.dy - p) / 2);
+        P.tdx[c][j] = (int8_t)((t.dx - q) / 2);
+        // empty parity view (dimension of size 1 in the tensor): such taps only ever read padding
+        if ((p == 1 && g.IH < 2) || (q == 1 && g.IW < 2)) { P.tdy[c][j] = 64; P.tdx[c][j] = 64; }
+      } else {
+        P.tview[c][j] = 0; P.tdy[c][j] = t.dy; P.tdx[c][j] = t.dx;
+      }
+      P.twt[c][j] = t.wtap;
+    }
+  (void)geom_kind;
+  const int BN = Nout % 128 == 0 ? 128 : 64;
+  dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
+  if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
+  return launch_tapgemm<64, 4>(P, grid, st);
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const WgradParams& P, dim3 grid, cudaStream_t st) {
+  using SM = WgradSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapwgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  tapwgrad_tc_kernel<BN, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  return finish_launch();
+}
+
+int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
+                const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st) {
+  if (D0 % 128 != 0 || D1 % 64 != 0 || lds % 8 != 0 || ldl % 8 != 0 || !al16(S) || !al16(L)) return STCGAN_EUNSUPPORTED;
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  choose_tile(64, SW, SH, N, &P.wt, &P.ht, &P.nt);
+  P.tiles_w = (SW + P.wt - 1) / P.wt; P.tiles_h = (SH + P.ht - 1) / P.ht; P.tiles_n = (N + P.nt - 1) / P.nt;
+  P.D0 = D0; P.D1 = D1; P.G = G;
+  const int BN = D1 % 128 == 0 ? 128 : 64;
+  const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int out_tiles = (D0 / 128) * (D1 / BN) * 16;
+  int splits = (2 * 148 + out_tiles - 1) / out_tiles;      // aim for ~2 CTAs per SM
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits < 1) splits = 1;
+  P.tiles_per_split = (total_tiles + splits - 1) / splits;
+  splits = (total_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
+
+  const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(S);
+  const __nv_bfloat16* lb = static_cast<const __nv_bfloat16*>(L);
+  int rc = encode_nhwc(&P.smap, sb, D0, SW, SH, N, lds, (long long)SW * lds, (long long)SH * SW * lds, P.wt, P.ht, P.nt);
+  if (rc) return rc;
+  const long long sn = (long long)LH * LW * ldl;
+  const int stride = geom == STCGAN_GEOM_WIN_S2 ? 2 : 1;
+  if (stride == 1) {
+    rc = encode_nhwc(&P.lmap[0], lb, D1, LW, LH, N, ldl, (long long)LW * ldl, sn, P.wt, P.ht, P.nt);
+    if (rc) return rc;
+    for (int v = 1; v < 4; ++v) P.lmap[v] = P.lmap[0];
+  } else {
+    for (int p = 0; p < 2; ++p)
+      for (int q = 0; q < 2; ++q) {
+        rc = encode_nhwc(&P.lmap[p * 2 + q], lb + ((long long)p * LW + q) * ldl, D1, (LW - q + 1) / 2, (LH - p + 1) / 2, N,
+                         2LL * ldl, 2LL * LW * ldl, sn, P.wt, P.ht, P.nt);
+        if (rc) return rc;
+      }
+  }
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      const int t = kh * 4 + kw, dy = kh - 1, dx = kw - 1;
+      if (stride == 2) {
+        const int p = dy & 1, q = dx & 1;
+        P.tview[t] = (int8_t)(p * 2 + q); P.tdy[t] = (int8_t)((dy - p) / 2); P.tdx[t] = (int8_t)((dx - q) / 2);
+        if ((p == 1 && LH < 2) || (q == 1 && LW < 2)) { P.tdy[t] = 64; P.tdx[t] = 64; }
+      } else {
+        P.tview[t] = 0; P.tdy[t] = (int8_t)dy; P.tdx[t] = (int8_t)dx;
+      }
+    }
+  dim3 grid((unsigned)((D0 / 128) * (D1 / BN)), 16, (unsigned)splits);
+  if (BN == 128) return launch_wgrad<128, 4>(P, grid, st);
+  return launch_wgrad<64, 4>(P, grid, st);
+}
+
+}  // namespace stcgan

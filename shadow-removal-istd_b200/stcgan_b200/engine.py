@@ -1,0 +1,201 @@
+"""Hand-scheduled ST-CGAN train step and inference on the kernel runtimes (no autograd).
+
+`STCGANEngine.train_step` executes exactly the step body of the reference trainer
+(CGAN.run_epoch, src/cgan.py:274-351, VisualLoss terms off):
+
+    D phase : C1_real = D1(x,m); m_pred = G1(x); C1_fake = D1(x, m_pred.detach());
+              C2_real = D2(x,m,y); y_pred = G2(x, m_pred); C2_fake = D2(x, m_pred.detach(), y_pred.detach());
+              D_loss = l2*D1_loss + l3*D2_loss; backward; Adam(D1+D2)
+    G phase : the four D passes again with the UPDATED discriminators (the two `real` ones only matter for
+              BatchNorm running statistics -- SURVEY appendix A -- and can be skipped behind a flag);
+              G_loss = L1(m_pred,m) + l1*L1(y_pred,y) + l2*adv(C1_fake) + l3*adv(C2_fake); backward through
+              D (dgrad only), G2 (its input gradient's mask channel flows into G1) and G1; Adam(G1+G2)
+
+Gradients stay in packed tap-major layout and are consumed in place by the fused Adam; under
+data parallelism (one process per GPU) the four flat gradient buffers are all-reduced with NCCL, the G2
+bucket while G1's backward is still running.  The whole step can be captured into ONE CUDA graph.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+from .optim import FusedAdam
+
+SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss")
+
+
+@dataclass
+class TrainConfig:
+    """Defaults of src/main.py:182-239; `ls` is what `args.D_loss_fn == "leastsqure"` evaluates to (always False)."""
+    lr_G: float = 5e-4
+    lr_D: float = 1e-4
+    beta1: float = 0.5
+    beta2: float = 0.999
+    lambda1: float = 5.0
+    lambda2: float = 0.5
+    lambda3: float = 0.5
+    ls: bool = False
+    skip_dead_real_passes: bool = False   # True drops the two G-phase `real` D passes (changes D's running stats only)
+
+
+class STCGANEngine:
+    def __init__(self, G1, G2, D1, D2, cfg: TrainConfig = TrainConfig(), process_group=None):
+        self.nets = dict(G1=G1, G2=G2, D1=D1, D2=D2)
+        self.cfg = cfg
+        for n in self.nets.values():
+            if not next(n.parameters()).is_cuda:
+                raise RuntimeError("STCGANEngine needs the modules on a CUDA device (no CPU fallback)")
+            n.train()
+        self.rt = {k: n.runtime() for k, n in self.nets.items()}
+        for rt in self.rt.values():
+            rt.ensure_packed()
+            rt.alloc_grads()
+        self.device = self.rt["G1"].device()
+        self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
+        self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
+        self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
+        self.optim_D.set_packed_grads({**self.rt["D1"].param_grad_views, **self.rt["D2"].param_grad_views})
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.optim_G.grad_scale = self.optim_D.grad_scale = 1.0 / self.world
+        self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._graph = None
+        self._static = None
+        self.last = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _allreduce(self, names, async_op=False):
+        if self.world == 1:
+            return []
+        import torch.distributed as dist
+        return [dist.all_reduce(self.rt[n].flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op) for n in names]
+
+    def _step_impl(self, x, m, y):
+        cfg, rt = self.cfg, self.rt
+        kind = ops.KIND_BCE if cfg.ls else ops.KIND_MSE
+        real, fake = 1.0, (-1.0 if cfg.ls else 0.0)
+        newg = lambda t: torch.empty_like(t)
+        # ================= D phase (cgan.py:278-305) =================
+        rt["D1"].zero_grads(); rt["D2"].zero_grads()
+        c1r, w1r = rt["D1"].forward([x, m], True)
+        mp, wg1 = rt["G1"].forward([x], True)
+        c1f, w1f = rt["D1"].forward([x, mp], True)
+        c2r, w2r = rt["D2"].forward([x, m, y], True)
+        yp, wg2 = rt["G2"].forward([x, mp], True)
+        c2f, w2f = rt["D2"].forward([x, mp, yp], True)
+        self.losses.zero_()
+        d1r, d1f, d2r, d2f = newg(c1r), newg(c1f), newg(c2r), newg(c2f)
+        ops.fused_loss([
+            dict(kind=kind, a=c1r, grad=d1r, target=real, weight=0.5 * cfg.lambda2, loss_weight=0.5, slot=0),
+            dict(kind=kind, a=c1f, grad=d1f, target=fake, weight=0.5 * cfg.lambda2, loss_weight=0.5, slot=0),
+            dict(kind=kind, a=c2r, grad=d2r, target=real, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
+            dict(kind=kind, a=c2f, grad=d2f, target=fake, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
+        ], self.losses)
+        rt["D1"].backward(w1r, d1r, False); rt["D1"].backward(w1f, d1f, False)
+        rt["D2"].backward(w2r, d2r, False); rt["D2"].backward(w2f, d2f, False)
+        del w1r, w1f, w2r, w2f
+        self._allreduce(("D1", "D2"))
+        self.optim_D.step()                                   # cgan.py:305
+        # ================= G phase (cgan.py:316-351) =================
+        rt["G1"].zero_grads(); rt["G2"].zero_grads()
+        if not cfg.skip_dead_real_passes:
+            rt["D1"].forward([x, m], True)                    # cgan.py:321 (BatchNorm running-stat side effect only)
+            rt["D2"].forward([x, m, y], True)                 # cgan.py:323
+        c1f, w1f = rt["D1"].forward([x, mp], True)            # cgan.py:322
+        c2f, w2f = rt["D2"].forward([x, mp, yp], True)        # cgan.py:324
+        dm, dy, d1f, d2f = newg(mp), newg(yp), newg(c1f), newg(c2f)
+        ops.fused_loss([
+            dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),
+            dict(kind=ops.KIND_L1, a=yp, b=y, grad=dy, weight=cfg.lambda1, loss_weight=1.0, slot=5),
+            dict(kind=kind, a=c1f, grad=d1f, target=real, weight=cfg.lambda2, loss_weight=1.0, slot=2),
+            dict(kind=kind, a=c2f, grad=d2f, target=real, weight=cfg.lambda3, loss_weight=1.0, slot=3),
+        ], self.losses)
+        di2 = rt["D2"].backward(w2f, d2f, True, param_grads=False)      # dgrad only: D is frozen (cgan.py:317-318)
+        ops.unpack_input_grad(di2, 4, 3, dy, True)
+        ops.unpack_input_grad(di2, 3, 1, dm, True)
+        di1 = rt["D1"].backward(w1f, d1f, True, param_grads=False)
+        ops.unpack_input_grad(di1, 3, 1, dm, True)
+        dig2 = rt["G2"].backward(wg2, dy, True)
+        pending = self._allreduce(("G2",), async_op=True)     # overlaps G1's backward
+        ops.unpack_input_grad(dig2, 3, 1, dm, True)           # G2's input gradient, mask channel (cgan.py:286)
+        rt["G1"].backward(wg1, dm, False)
+        pending += self._allreduce(("G1",), async_op=True)
+        for wk in pending:
+            wk.wait()
+        self.optim_G.step()                                   # cgan.py:351
+        for r in rt.values():
+            r.ensure_packed()                                 # re-pack the updated weights for the next step
+        return mp, yp
+
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, x, m, y):
+        """x [B,3,H,W], m [B,1,H,W], y [B,3,H,W]: float32 CUDA tensors in [-1,1].  Returns the device tensor of
+        losses (index with SLOTS); nothing is synchronised."""
+        for t in (x, m, y):
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise RuntimeError("train_step expects float32 CUDA tensors")
+        mp, yp = self._step_impl(x.contiguous(), m.contiguous(), y.contiguous())
+        self.last = dict(m_pred=mp, y_pred=yp)
+        return self.losses
+
+    def capture(self, x, m, y, warmup=3):
+        """Capture the train step into a CUDA graph for inputs of this shape (static buffers)."""
+        if self.world > 1:
+            raise RuntimeError("CUDA-graph capture is used for single-GPU steps; multi-GPU steps run eagerly")
+        self._static = tuple(t.clone() for t in (x, m, y))
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_impl(*self._static)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.optim_D.prepare(); self.optim_G.prepare()
+        g = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(g):
+            mp, yp = self._step_impl(*self._static)
+        self.graph_launches = _lib.launch_count() - before
+        self._graph = g
+        self.last = dict(m_pred=mp, y_pred=yp)
+        return g
+
+    def replay(self, x=None, m=None, y=None):
+        """Run the captured step (optionally on new inputs of the captured shape)."""
+        if self._graph is None:
+            raise RuntimeError("call capture() first")
+        for dst, src in zip(self._static, (x, m, y)):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
+        return self.losses
+
+    def loss_dict(self, losses=None):
+        v = (self.losses if losses is None else losses).detach().cpu().tolist()
+        d = dict(zip(SLOTS, v))
+        c = self.cfg
+        d["D_loss"] = c.lambda2 * d["D1_loss"] + c.lambda3 * d["D2_loss"]
+        d["G_loss"] = d["data1_loss"] + c.lambda1 * d["data2_loss"] + c.lambda2 * d["G1_loss"] + c.lambda3 * d["G2_loss"]
+        return d
+
+
+@torch.no_grad()
+def infer(G1, G2, x, quantize=True):
+    """CGAN.infer core (src/cgan.py:437-446 + utils.float2uint): eval-mode G1 -> G2; returns
+    (m_pred, y_pred [NCHW fp32], m_u8, y_u8 [N,H,W,C] uint8 or None)."""
+    if G1.training or G2.training:
+        raise RuntimeError("infer() expects G1.eval(); G2.eval() like the reference (cgan.py:422-423)")
+    rt1, rt2 = G1.runtime(), G2.runtime()
+    x = x.contiguous()
+    mp, _ = rt1.forward([x], False)
+    yp, _ = rt2.forward([x, mp], False)
+    if not quantize:
+        return mp, yp, None, None
+    return mp, yp, ops.float2uint_hwc(mp), ops.float2uint_hwc(yp)

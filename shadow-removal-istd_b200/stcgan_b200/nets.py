@@ -1,0 +1,390 @@
+"""Whole-network forward/backward schedules for the ST-CGAN generator (8-level U-Net) and the
+70x70 PatchGAN discriminator, expressed as sequences of the C-ABI kernels in `ops`.
+
+What the reference does with nested nn.Sequential + autograd (src/models/stcgan_g.py:55-57,120-132;
+src/models/stcgan_d.py:57-58) is here an explicit schedule over NHWC buffers:
+
+  * skip concatenations are never produced by a copy: the encoder's BN/activation pass writes
+    relu(x_k) straight into the left half of the decoder's input buffer, the decoder's BN pass
+    writes relu(bn(u_{k+1})) into the right half (cropped, for odd sizes);
+  * the in-place LeakyReLU / ReLU pair on the skip becomes two outputs of one pass;
+  * odd spatial sizes are handled by letting the convolution read its zero padding out of
+    range (no F.pad copy) and by cropping inside the BN/activation pass.
+
+Nothing here computes with torch; torch only owns the buffers.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BACKEND_FFMA, BACKEND_TC, GEOM_PARITY,
+                   GEOM_WIN_S1, GEOM_WIN_S1_FLIP, GEOM_WIN_S2)
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+class ConvOp:
+    """One Conv2d(4,s,1) / ConvTranspose2d(4,2,1) weight with its packed copies and packed gradient."""
+
+    def __init__(self, kind, weight, bias):
+        assert kind in ("conv2", "conv1", "convT")
+        self.kind, self.weight, self.bias = kind, weight, bias
+        self.d0, self.d1 = int(weight.shape[0]), int(weight.shape[1])
+        self.cin, self.cout = (self.d0, self.d1) if kind == "convT" else (self.d1, self.d0)
+        self.p1 = self.p2 = None          # packed weights [16,d0,d1], [16,d1,d0]
+        self.g = None                     # packed gradient [16,d0,d1] fp32 (view into the net's flat buffer)
+        self.gb = None                    # bias gradient
+        self.version = None
+        self.use_tc = False
+
+    # ---- packing ------------------------------------------------------------------------
+    def ensure_packed(self, act_dtype, force=False):
+        w = self.weight
+        ver = (w._version, w.data_ptr(), act_dtype)
+        if force or ver != self.version or self.p1 is None:
+            if self.p1 is None or self.p1.dtype != act_dtype or self.p1.device != w.device:
+                self.p1 = torch.empty((16, self.d0, self.d1), dtype=act_dtype, device=w.device)
+                self.p2 = torch.empty((16, self.d1, self.d0), dtype=act_dtype, device=w.device)
+            ops.pack_weight(w.detach() if w.is_contiguous() else w.detach().contiguous(), self.p1, self.p2)
+            self.version = ver
+        self.use_tc = act_dtype == torch.bfloat16
+
+    def _backend_conv(self, k, nout, plain_epilogue=True):
+        return BACKEND_TC if (self.use_tc and plain_epilogue and ops.tc_eligible_conv(k, nout)) else BACKEND_FFMA
+
+    # ---- the three GEMMs ------------------------------------------------------------------
+    def out_size(self, ih, iw):
+        if self.kind == "conv2":
+            return (ih + 2 - 4) // 2 + 1, (iw + 2 - 4) // 2 + 1
+        if self.kind == "conv1":
+            return ih - 1, iw - 1
+        return ih * 2, iw * 2
+
+    def forward(self, x, oh, ow, *, out=None, out_nchw=None, act=ACT_NONE, use_bias=True):
+        geom = {"conv2": GEOM_WIN_S2, "conv1": GEOM_WIN_S1, "convT": GEOM_PARITY}[self.kind]
+        wp = self.p2 if self.kind == "convT" else self.p1
+        bias = self.bias.detach() if (self.bias is not None and use_bias) else None
+        plain = out_nchw is None and act in (ACT_NONE, ACT_LEAKY, ACT_RELU)
+        return ops.tapconv(geom, x, wp, self.cout, oh, ow, bias=bias, act=act, out=out, out_nchw=out_nchw,
+                           backend=self._backend_conv(self.cin, self.cout, plain))
+
+    def dgrad(self, g, ih, iw, *, out=None):
+        """gradient w.r.t. the layer input [N, ih, iw, cin] from g = gradient w.r.t. the layer output."""
+        geom = {"conv2": GEOM_PARITY, "conv1": GEOM_WIN_S1_FLIP, "convT": GEOM_WIN_S2}[self.kind]
+        wp = self.p1 if self.kind == "convT" else self.p2
+        return ops.tapconv(geom, g, wp, self.cin, ih, iw, out=out, backend=self._backend_conv(self.cout, self.cin))
+
+    def wgrad(self, x, g):
+        """accumulate the packed weight gradient from the layer input x and output gradient g."""
+        if self.kind == "convT":
+            s, l, geom = x, g, GEOM_WIN_S2
+        else:
+            s, l, geom = g, x, (GEOM_WIN_S2 if self.kind == "conv2" else GEOM_WIN_S1)
+        backend = BACKEND_TC if (self.use_tc and ops.tc_eligible_wgrad(self.d0, self.d1)) else BACKEND_FFMA
+        ops.tapwgrad(geom, s, l, self.g, backend=backend)
+        if self.bias is not None and self.gb is not None:
+            ops.colsum(g, self.gb)
+
+
+class BNOp:
+    """BatchNorm2d parameters/buffers + per-pass scratch handling."""
+
+    def __init__(self, bn_module):
+        self.m = bn_module
+        self.c = bn_module.num_features
+        self.ggamma = self.gbeta = None     # fp32 gradient views
+
+    def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE):
+        """stats (training) -> finalize -> apply.  scratch: dict with 'acc' (f64 [2,C]), 'mi', 'ss' (f32 [2,C])."""
+        m = self.m
+        n, h, w, _ = y.shape
+        if training:
+            if n * h * w <= 1:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, self.c, h, w]}")
+            ops.bn_stats(y, scratch["acc"])
+            use_running = m.track_running_stats and m.running_mean is not None
+            ops.bn_finalize(scratch["acc"], n * h * w, m.weight.detach(), m.bias.detach(),
+                            m.running_mean if use_running else None, m.running_var if use_running else None,
+                            BN_MOMENTUM if m.momentum is None else m.momentum, m.eps, True, scratch["mi"], scratch["ss"])
+            if use_running and m.num_batches_tracked is not None:
+                m.num_batches_tracked.add_(1)
+        else:
+            ops.bn_finalize(None, n * h * w, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var,
+                            0.0, m.eps, False, scratch["mi"], scratch["ss"])
+        ops.bn_act_apply(y, scratch["ss"], out1, act1, out2, act2)
+
+    def backward(self, y, scratch, training, g1, act1, g2, act2, dy, want_param_grads):
+        scratch["acc"].zero_()
+        ops.bn_act_bwd(y, scratch["ss"], scratch["mi"], self.m.weight.detach(), training, g1, act1, g2, act2,
+                       scratch["acc"], dy, self.ggamma if want_param_grads else None,
+                       self.gbeta if want_param_grads else None)
+
+
+def _bn_scratch(c, device):
+    return {"acc": torch.zeros((2, c), dtype=torch.float64, device=device),
+            "mi": torch.empty((2, c), dtype=torch.float32, device=device),
+            "ss": torch.empty((2, c), dtype=torch.float32, device=device)}
+
+
+class _NetRuntimeBase:
+    """Holds ConvOps/BNOps of one network, the flat packed-gradient buffer and the Adam views."""
+
+    def __init__(self, convs, bns, precision):
+        self.convs, self.bns = convs, bns
+        self.precision = precision
+        self.act_dtype = ops.DTYPES[precision][1]
+        self.flat_grad = None
+        self.param_grad_views = {}     # id(param) -> (view, d0, d1)  (d0 = 0 for non-packed gradients)
+
+    def device(self):
+        return self.convs[0].weight.device
+
+    def ensure_packed(self, force=False):
+        for c in self.convs:
+            c.ensure_packed(self.act_dtype, force)
+
+    def alloc_grads(self):
+        """One flat fp32 buffer: packed conv-weight gradients, then bias / BN gradients."""
+        if self.flat_grad is not None and self.flat_grad.device == self.device():
+            return
+        sizes = []
+        for c in self.convs:
+            sizes.append(("w", c, 16 * c.d0 * c.d1))
+        for c in self.convs:
+            if c.bias is not None:
+                sizes.append(("b", c, c.cout))
+        for b in self.bns:
+            sizes.append(("gamma", b, b.c))
+            sizes.append(("beta", b, b.c))
+        total = sum((s + 3) // 4 * 4 for _, _, s in sizes)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device())
+        off = 0
+        for kind, obj, s in sizes:
+            v = self.flat_grad[off:off + s]
+            if kind == "w":
+                obj.g = v
+                self.param_grad_views[id(obj.weight)] = (v, obj.d0, obj.d1)
+            elif kind == "b":
+                obj.gb = v
+                self.param_grad_views[id(obj.bias)] = (v, 0, 0)
+            elif kind == "gamma":
+                obj.ggamma = v
+                self.param_grad_views[id(obj.m.weight)] = (v, 0, 0)
+            else:
+                obj.gbeta = v
+                self.param_grad_views[id(obj.m.bias)] = (v, 0, 0)
+            off += (s + 3) // 4 * 4
+
+    def zero_grads(self):
+        self.alloc_grads()
+        self.flat_grad.zero_()
+
+    def grads_in_parameter_layout(self, params):
+        """torch-layout gradients for autograd (conv weights are un-packed by a kernel)."""
+        out = []
+        for p in params:
+            v, d0, d1 = self.param_grad_views[id(p)]
+            out.append(ops.unpack_grad(v, d0, d1) if d0 > 0 else v.clone().view(p.shape))
+        return out
+
+
+# =================================================================================================
+# Generator
+# =================================================================================================
+class GeneratorRuntime(_NetRuntimeBase):
+    def __init__(self, downs, down_bns, ups, up_bns, in_channels, out_channels, precision):
+        """downs[k-1], ups[k-1]: ConvOps of level k (1 = outermost); down_bns/up_bns: BNOp or None per level."""
+        self.L = len(downs)
+        self.downs, self.ups, self.down_bns, self.up_bns = downs, ups, down_bns, up_bns
+        self.cin, self.cout = in_channels, out_channels
+        self.cpad = max(4, (in_channels + 3) // 4 * 4)
+        convs = list(downs) + list(ups)
+        bns = [b for b in down_bns if b is not None] + [b for b in up_bns if b is not None]
+        super().__init__(convs, bns, precision)
+
+    def sizes(self, h, w):
+        """spatial size of every level: s[0] = input, s[k] = output of down conv k."""
+        s = [(h, w)]
+        for k in range(1, self.L + 1):
+            ph, pw = s[-1]
+            if k > 1:
+                ph, pw = ph + ph % 2, pw + pw % 2        # F.pad to even (stcgan_g.py:126-130)
+            s.append(self.downs[k - 1].out_size(ph, pw))
+        return s
+
+    def forward(self, sources, training):
+        """sources: list of NCHW fp32 tensors concatenated along channels (the torch.cat of cgan.py:286).
+        Returns (out NCHW fp32, workspace)."""
+        self.ensure_packed()
+        dt, dev, L = self.act_dtype, self.device(), self.L
+        inp = ops.pack_input(sources, self.cpad, dt)
+        n, h, w, _ = inp.shape
+        s = self.sizes(h, w)
+        ws = {"inp": inp, "s": s, "training": training, "y": [None] * (L + 1), "a": [None] * (L + 1),
+              "cat": [None] * (L + 1), "uy": [None] * (L + 2), "bn_d": [None] * (L + 1), "bn_u": [None] * (L + 2)}
+        C = [None] + [d.cout for d in self.downs]
+        new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        # ---- encoder
+        x = inp[..., :self.cin]
+        for k in range(1, L + 1):
+            hk, wk = s[k]
+            y = self.downs[k - 1].forward(x, hk, wk)
+            ws["y"][k] = y
+            if k < L:
+                a = new(hk, wk, C[k])
+                cat = new(hk, wk, 2 * C[k])
+                ws["a"][k], ws["cat"][k] = a, cat
+                if self.down_bns[k - 1] is not None:
+                    sc = _bn_scratch(C[k], dev)
+                    ws["bn_d"][k] = sc
+                    self.down_bns[k - 1].forward(y, sc, training, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU)
+                else:
+                    ops.bn_act_apply(y, None, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU)
+                x = a
+            else:
+                r = new(hk, wk, C[k])
+                ws["a"][k] = r
+                ops.bn_act_apply(y, None, r, ACT_RELU)
+                x = r
+        # ---- decoder
+        for k in range(L, 1, -1):
+            hk, wk = s[k]
+            up = self.ups[k - 1]
+            uy = up.forward(x, 2 * hk, 2 * wk)
+            ws["uy"][k] = uy
+            sc = _bn_scratch(up.cout, dev)
+            ws["bn_u"][k] = sc
+            dst = ws["cat"][k - 1]
+            self.up_bns[k - 1].forward(uy, sc, training, dst[..., C[k - 1]:], ACT_RELU)   # crops to dst's H, W
+            x = dst
+        h1, w1 = s[1]
+        out = torch.empty((n, self.cout, 2 * h1, 2 * w1), dtype=torch.float32, device=dev)
+        self.ups[0].forward(x, 2 * h1, 2 * w1, out_nchw=out, act=ACT_TANH)
+        ws["out"] = out
+        return out, ws
+
+    def backward(self, ws, dout, need_input_grad, param_grads=True):
+        """dout: NCHW fp32 gradient of the output.  Accumulates parameter gradients into the flat buffer;
+        returns the NHWC gradient of the packed input (or None)."""
+        dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
+        training = ws["training"]
+        n = ws["inp"].shape[0]
+        C = [None] + [d.cout for d in self.downs]
+        new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        # ---- outermost up conv (+Tanh)
+        g = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt)
+        up = self.ups[0]
+        if param_grads:
+            up.wgrad(ws["cat"][1], g)
+        dcat = up.dgrad(g, *s[1])
+        # ---- decoder, outside-in
+        for k in range(2, L + 1):
+            up, bn, sc = self.ups[k - 1], self.up_bns[k - 1], ws["bn_u"][k]
+            uy = ws["uy"][k]
+            guy = torch.empty_like(uy)
+            bn.backward(uy, sc, training, dcat[..., C[k - 1]:], ACT_RELU, None, ACT_NONE, guy, param_grads)
+            x_in = ws["cat"][k] if k < L else ws["a"][L]
+            if param_grads:
+                up.wgrad(x_in, guy)
+            dcat_prev, dcat = dcat, up.dgrad(guy, *s[k])
+            ws.setdefault("dcat", {})[k - 1] = dcat_prev
+        dcats = ws["dcat"]
+        # ---- encoder, inside-out.  `da` = gradient w.r.t. the activated tensor feeding the next down conv
+        da = dcat                       # at k = L: gradient w.r.t. relu(x_L)
+        for k in range(L, 0, -1):
+            y = ws["y"][k]
+            gy = torch.empty_like(y)
+            if k == L:
+                ops.bn_act_bwd(y, None, None, None, training, da, ACT_RELU, None, ACT_NONE, None, gy, None, None)
+            else:
+                skip_g = dcats[k][..., :C[k]]
+                bn = self.down_bns[k - 1]
+                if bn is not None:
+                    bn.backward(y, ws["bn_d"][k], training, da, ACT_LEAKY, skip_g, ACT_RELU, gy, param_grads)
+                else:
+                    ops.bn_act_bwd(y, None, None, None, training, da, ACT_LEAKY, skip_g, ACT_RELU, None, gy, None, None)
+            down = self.downs[k - 1]
+            x_in = ws["a"][k - 1] if k > 1 else ws["inp"][..., :self.cin]
+            if param_grads:
+                down.wgrad(x_in, gy)
+            if k > 1:
+                da = down.dgrad(gy, *s[k - 1])
+            elif need_input_grad:
+                dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
+                down.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                return dinp
+        return None
+
+
+# =================================================================================================
+# Discriminator
+# =================================================================================================
+class DiscriminatorRuntime(_NetRuntimeBase):
+    def __init__(self, convs, bns, in_channels, use_sigmoid, precision):
+        """convs: ConvOps in order; bns[i]: BNOp or None following conv i."""
+        self.layers, self.layer_bns = convs, bns
+        self.cin = in_channels
+        self.cpad = max(4, (in_channels + 3) // 4 * 4)
+        self.use_sigmoid = use_sigmoid
+        super().__init__(list(convs), [b for b in bns if b is not None], precision)
+
+    def forward(self, sources, training):
+        self.ensure_packed()
+        dt, dev = self.act_dtype, self.device()
+        inp = ops.pack_input(sources, self.cpad, dt)
+        n, h, w, _ = inp.shape
+        nl = len(self.layers)
+        ws = {"inp": inp, "training": training, "y": [None] * nl, "a": [None] * nl, "bn": [None] * nl, "s": [(h, w)]}
+        x = inp[..., :self.cin]
+        for i, conv in enumerate(self.layers):
+            oh, ow = conv.out_size(*ws["s"][-1])
+            if oh < 1 or ow < 1:
+                raise RuntimeError(f"input {h}x{w} too small for the PatchGAN discriminator")
+            ws["s"].append((oh, ow))
+            if i == nl - 1:
+                out = torch.empty((n, conv.cout, oh, ow), dtype=torch.float32, device=dev)
+                conv.forward(x, oh, ow, out_nchw=out, act=ACT_SIGMOID if self.use_sigmoid else ACT_NONE)
+                ws["out"] = out
+                return out, ws
+            bn = self.layer_bns[i]
+            if bn is None:
+                # bias + LeakyReLU fused into the conv epilogue; sign(a) == sign(pre-activation) serves the backward
+                a = conv.forward(x, oh, ow, act=ACT_LEAKY)
+                ws["a"][i] = a
+            else:
+                y = conv.forward(x, oh, ow)
+                a = torch.empty_like(y)
+                sc = _bn_scratch(conv.cout, dev)
+                ws["y"][i], ws["a"][i], ws["bn"][i] = y, a, sc
+                bn.forward(y, sc, training, a, ACT_LEAKY)
+            x = a
+
+    def backward(self, ws, dout, need_input_grad, param_grads=True):
+        dt, dev = self.act_dtype, self.device()
+        training, s = ws["training"], ws["s"]
+        nl = len(self.layers)
+        n = ws["inp"].shape[0]
+        g = ops.out_act_bwd(ACT_SIGMOID if self.use_sigmoid else ACT_NONE, ws["out"], dout, dt)
+        for i in range(nl - 1, -1, -1):
+            conv = self.layers[i]
+            x_in = ws["a"][i - 1] if i > 0 else ws["inp"][..., :self.cin]
+            if i < nl - 1:
+                bn = self.layer_bns[i]
+                if bn is None:
+                    gy = torch.empty_like(ws["a"][i])
+                    ops.bn_act_bwd(ws["a"][i], None, None, None, training, g, ACT_LEAKY, None, ACT_NONE, None, gy, None, None)
+                else:
+                    gy = torch.empty_like(ws["y"][i])
+                    bn.backward(ws["y"][i], ws["bn"][i], training, g, ACT_LEAKY, None, ACT_NONE, gy, param_grads)
+            else:
+                gy = g
+            if param_grads:
+                conv.wgrad(x_in, gy)
+            if i > 0:
+                g = conv.dgrad(gy, *s[i])
+            elif need_input_grad:
+                dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
+                conv.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                return dinp
+        return None

@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI.  torch is used for device memory and streams only.
+
+Activations are NHWC tensors (`torch.bfloat16` in "bf16" mode, `torch.float32` in "fp32" mode);
+a channel slice of a wider NHWC buffer is a normal torch view (`buf[..., :C]`), its pixel pitch
+is read from `stride(2)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BACKEND_FFMA, BACKEND_TC, BF16, F32,
+                   GEOM_PARITY, GEOM_WIN_S1, GEOM_WIN_S1_FLIP, GEOM_WIN_S2, LossTerm, check)
+
+DTYPES = {"fp32": (F32, torch.float32), "bf16": (BF16, torch.bfloat16)}
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stcgan_b200 kernels need CUDA tensors (no CPU fallback exists)")
+
+
+def _nhwc(t: torch.Tensor):
+    """(N, H, W, C, pitch) of an NHWC tensor or channel-slice view."""
+    assert t.dim() == 4, "expected an NHWC tensor"
+    n, h, w, c = t.shape
+    assert c == 1 or t.stride(3) == 1, "expected an NHWC tensor with unit channel stride"
+    # strides of size-1 dimensions are arbitrary in torch: derive the pixel pitch from the first dimension that has one
+    if w > 1:
+        ld = t.stride(2)
+    elif h > 1:
+        ld = t.stride(1)
+    elif n > 1:
+        ld = t.stride(0)
+    else:
+        ld = c
+    assert ld >= c, "NHWC view: pixel pitch smaller than the channel count"
+    assert (h == 1 or t.stride(1) == w * ld) and (n == 1 or t.stride(0) == h * w * ld), "NHWC view must be pixel-contiguous"
+    return n, h, w, c, ld
+
+
+def tc_eligible_conv(k: int, nout: int) -> bool:
+    return k % 64 == 0 and nout % 64 == 0
+
+
+def tc_eligible_wgrad(d0: int, d1: int) -> bool:
+    return d0 % 128 == 0 and d1 % 64 == 0
+
+
+def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out_nchw=None, backend=BACKEND_FFMA):
+    """out[N,OH,OW,nout] = tap-GEMM(x, wp).  `out` may be a channel-slice view; `out_nchw` (fp32 [N,nout,OH,OW])
+    selects the NCHW epilogue instead."""
+    _need_cuda(x, wp)
+    n, ih, iw, k, ldx = _nhwc(x)
+    lib = _lib.load()
+    if out_nchw is not None:
+        y, ldy, nchw = out_nchw, nout, 1
+        assert out_nchw.dtype == torch.float32 and out_nchw.is_contiguous()
+    else:
+        if out is None:
+            out = torch.empty((n, oh, ow, nout), dtype=x.dtype, device=x.device)
+        _, _, _, _, ldy = _nhwc(out)
+        y, nchw = out, 0
+    check(lib.stcgan_tapconv(geom, _code(x), backend, x.data_ptr(), n, ih, iw, k, ldx, wp.data_ptr(),
+                             None if bias is None else bias.data_ptr(), act, y.data_ptr(), oh, ow, nout, ldy, nchw,
+                             _stream()), "stcgan_tapconv")
+    return y
+
+
+def tapwgrad(geom, s, l, g, *, backend=BACKEND_FFMA):
+    """g[16, D0, D1] (fp32) += wgrad(S small-grid tensor, L large-grid tensor)."""
+    _need_cuda(s, l, g)
+    n, sh, sw, d0, lds = _nhwc(s)
+    n2, lh, lw, d1, ldl = _nhwc(l)
+    assert n == n2 and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == 16 * d0 * d1
+    check(_lib.load().stcgan_tapwgrad(geom, _code(s), backend, s.data_ptr(), n, sh, sw, d0, lds, l.data_ptr(), lh, lw,
+                                      d1, ldl, g.data_ptr(), _stream()), "stcgan_tapwgrad")
+    return g
+
+
+def pack_weight(w, p1, p2):
+    """w [d0, d1, 4, 4] fp32 -> p1 [16, d0, d1], p2 [16, d1, d0] (either may be None)."""
+    _need_cuda(w)
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    d0, d1 = w.shape[0], w.shape[1]
+    ref = p1 if p1 is not None else p2
+    check(_lib.load().stcgan_pack_weight(_code(ref), w.data_ptr(), d0, d1, None if p1 is None else p1.data_ptr(),
+                                         None if p2 is None else p2.data_ptr(), _stream()), "stcgan_pack_weight")
+
+
+def unpack_grad(g, d0, d1, grad=None, accumulate=False):
+    _need_cuda(g)
+    if grad is None:
+        grad = torch.empty((d0, d1, 4, 4), dtype=torch.float32, device=g.device)
+    check(_lib.load().stcgan_unpack_grad(g.data_ptr(), d0, d1, grad.data_ptr(), int(accumulate), _stream()),
+          "stcgan_unpack_grad")
+    return grad
+
+
+def bn_stats(y, acc):
+    n, h, w, c, ld = _nhwc(y)
+    check(_lib.load().stcgan_bn_stats(_code(y), y.data_ptr(), n * h * w, c, ld, acc.data_ptr(), _stream()), "stcgan_bn_stats")
+
+
+def bn_finalize(acc, count, gamma, beta, rmean, rvar, momentum, eps, training, mean_invstd, scale_shift):
+    c = gamma.numel()
+    check(_lib.load().stcgan_bn_finalize(None if acc is None else acc.data_ptr(), count, c, gamma.data_ptr(), beta.data_ptr(),
+                                         None if rmean is None else rmean.data_ptr(),
+                                         None if rvar is None else rvar.data_ptr(), momentum, eps, int(training),
+                                         mean_invstd.data_ptr(), scale_shift.data_ptr(), _stream()), "stcgan_bn_finalize")
+
+
+def bn_act_apply(y, scale_shift, out1, act1, out2=None, act2=ACT_NONE):
+    n, h, w, c, ldy = _nhwc(y)
+    n1, hc, wc, c1, ld1 = _nhwc(out1)
+    assert c1 == c and n1 == n
+    ld2 = 0
+    if out2 is not None:
+        _, h2, w2, c2, ld2 = _nhwc(out2)
+        assert (h2, w2, c2) == (hc, wc, c)
+    check(_lib.load().stcgan_bn_act_apply(_code(y), y.data_ptr(), n, h, w, c, ldy,
+                                          None if scale_shift is None else scale_shift.data_ptr(), hc, wc,
+                                          out1.data_ptr(), ld1, act1, None if out2 is None else out2.data_ptr(), ld2, act2,
+                                          _stream()), "stcgan_bn_act_apply")
+
+
+def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2, acc, dy, dgamma, dbeta):
+    """Two-pass BN(+activation) backward; with scale_shift None this is the plain activation backward."""
+    n, h, w, c, ldy = _nhwc(y)
+    _, hc, wc, _, ldg1 = _nhwc(g1)
+    ldg2 = 0
+    if g2 is not None:
+        _, h2, w2, _, ldg2 = _nhwc(g2)
+        assert (h2, w2) == (hc, wc)
+    _, _, _, _, lddy = _nhwc(dy)
+    lib = _lib.load()
+    p = lambda t: None if t is None else t.data_ptr()
+    if scale_shift is not None and training:
+        check(lib.stcgan_bn_act_bwd_reduce(_code(y), y.data_ptr(), n, h, w, c, ldy, scale_shift.data_ptr(),
+                                           mean_invstd.data_ptr(), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2,
+                                           acc.data_ptr(), _stream()), "stcgan_bn_act_bwd_reduce")
+    elif scale_shift is not None and dgamma is not None:
+        # eval-mode BN: parameter gradients still need the reductions
+        check(lib.stcgan_bn_act_bwd_reduce(_code(y), y.data_ptr(), n, h, w, c, ldy, scale_shift.data_ptr(),
+                                           mean_invstd.data_ptr(), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2,
+                                           acc.data_ptr(), _stream()), "stcgan_bn_act_bwd_reduce")
+    check(lib.stcgan_bn_act_bwd_apply(_code(y), y.data_ptr(), n, h, w, c, ldy, p(scale_shift), p(mean_invstd), p(gamma),
+                                      int(training), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2, p(acc),
+                                      dy.data_ptr(), lddy, p(dgamma), p(dbeta), _stream()), "stcgan_bn_act_bwd_apply")
+
+
+def colsum(g, out):
+    n, h, w, c, ld = _nhwc(g)
+    check(_lib.load().stcgan_colsum(_code(g), g.data_ptr(), n * h * w, c, ld, out.data_ptr(), _stream()), "stcgan_colsum")
+
+
+def pack_input(sources, cpad, dtype):
+    """NCHW fp32 sources (<= 3) -> one NHWC tensor with `cpad` channels (zero padded)."""
+    srcs = [s for s in sources]
+    _need_cuda(*srcs)
+    n, _, h, w = srcs[0].shape
+    for s in srcs:
+        assert s.dtype == torch.float32 and s.is_contiguous() and s.shape[0] == n and s.shape[2:] == (h, w)
+    out = torch.empty((n, h, w, cpad), dtype=dtype, device=srcs[0].device)
+    args = []
+    for i in range(3):
+        if i < len(srcs):
+            args += [srcs[i].data_ptr(), srcs[i].shape[1]]
+        else:
+            args += [None, 0]
+    check(_lib.load().stcgan_pack_input(_code(out), *args, n, h, w, out.data_ptr(), cpad, _stream()), "stcgan_pack_input")
+    return out
+
+
+def unpack_input_grad(g, coff, cn, grad_nchw, accumulate):
+    n, h, w, c, ldg = _nhwc(g)
+    assert grad_nchw.dtype == torch.float32 and grad_nchw.is_contiguous()
+    check(_lib.load().stcgan_unpack_input_grad(_code(g), g.data_ptr(), n, h, w, ldg, coff, cn, grad_nchw.data_ptr(),
+                                               int(accumulate), _stream()), "stcgan_unpack_input_grad")
+
+
+def nhwc_to_nchw(x):
+    n, h, w, c, ld = _nhwc(x)
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.load().stcgan_nhwc_to_nchw(_code(x), x.data_ptr(), n, h, w, c, ld, out.data_ptr(), _stream()), "stcgan_nhwc_to_nchw")
+    return out
+
+
+def nchw_to_nhwc(x, dtype):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+    check(_lib.load().stcgan_nchw_to_nhwc(_code(out), x.data_ptr(), n, h, w, c, out.data_ptr(), c, _stream()), "stcgan_nchw_to_nhwc")
+    return out
+
+
+def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None):
+    """gradient through the output activation, NCHW fp32 -> NHWC `dtype`."""
+    n, c, h, w = out_nchw.shape
+    assert dout_nchw.is_contiguous() and out_nchw.is_contiguous() and dout_nchw.dtype == torch.float32
+    g = torch.empty((n, h, w, c), dtype=dtype, device=out_nchw.device)
+    check(_lib.load().stcgan_out_act_bwd(_code(g), act, out_nchw.data_ptr(), dout_nchw.data_ptr(), n, h, w, c,
+                                         g.data_ptr(), c, _stream()), "stcgan_out_act_bwd")
+    return g
+
+
+KIND_L1, KIND_MSE, KIND_BCE = 0, 1, 2
+
+
+def fused_loss(terms, loss_out):
+    """terms: list of dict(kind, a, b=None, grad=None, target=0., weight=1., slot=0, accumulate=False)."""
+    arr = (LossTerm * len(terms))()
+    for i, t in enumerate(terms):
+        a = t["a"]
+        _need_cuda(a)
+        assert a.dtype == torch.float32 and a.is_contiguous()
+        arr[i].a = a.data_ptr()
+        b = t.get("b")
+        if b is not None:
+            assert b.dtype == torch.float32 and b.is_contiguous() and b.numel() == a.numel()
+        arr[i].b = None if b is None else b.data_ptr()
+        g = t.get("grad")
+        if g is not None:
+            assert g.dtype == torch.float32 and g.is_contiguous() and g.numel() == a.numel()
+        arr[i].grad = None if g is None else g.data_ptr()
+        arr[i].n = a.numel()
+        arr[i].target = float(t.get("target", 0.0))
+        arr[i].weight = float(t.get("weight", 1.0))
+        arr[i].loss_weight = float(t.get("loss_weight", t.get("weight", 1.0)))
+        arr[i].kind = int(t["kind"])
+        arr[i].slot = int(t.get("slot", 0))
+        arr[i].accumulate = int(bool(t.get("accumulate", False)))
+    check(_lib.load().stcgan_fused_loss(arr, len(terms), loss_out.data_ptr(), _stream()), "stcgan_fused_loss")
+
+
+def float2uint_hwc(x_nchw):
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    n, c, h, w = x_nchw.shape
+    out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x_nchw.device)
+    check(_lib.load().stcgan_float2uint_hwc(x_nchw.data_ptr(), n, c, h, w, out.data_ptr(), _stream()), "stcgan_float2uint_hwc")
+    return out
+
+
+def float2uint(x):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(_lib.load().stcgan_float2uint(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "stcgan_float2uint")
+    return out

@@ -1,0 +1,138 @@
+"""Fused multi-tensor Adam with torch.optim.Adam's state layout.
+
+Replaces `optim.Adam(params, lr, betas=(beta1, beta2))` of src/cgan.py:85-90 (eps 1e-8, no weight decay,
+no amsgrad).  `state_dict()` / `load_state_dict()` are inherited from torch.optim.Optimizer and produce the
+same structure as torch's Adam (`state[i] = {step, exp_avg, exp_avg_sq}`), so `checkpoint.tar`
+(src/cgan.py:490-523) round-trips.  One kernel launch updates every tensor of a param group; the step
+counter and bias corrections live on the device so the whole train step can be replayed as a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
+        if weight_decay != 0 or amsgrad:
+            raise NotImplementedError("FusedAdam implements the configuration the reference uses (no weight decay / amsgrad)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self._tables = {}        # group index -> dict(sig, table, blocks, nblocks, keep, hyper, hyper_host)
+        self._packed_grads = {}  # id(param) -> (flat fp32 view, d0, d1): engine-provided packed gradients
+        self.grad_scale = 1.0
+
+    def set_packed_grads(self, views):
+        """Engine hook: gradients that live in packed [16][d0][d1] layout instead of `p.grad`."""
+        self._packed_grads = dict(views)
+        self._tables.clear()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables.clear()
+
+    def _state_for(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)     # host counter, like torch's default Adam
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _grad_of(self, p):
+        if id(p) in self._packed_grads:
+            return self._packed_grads[id(p)]
+        if p.grad is not None:
+            return p.grad, 0, 0
+        return None
+
+    def _signature(self, group):
+        sig = []
+        for p in group["params"]:
+            g = self._grad_of(p)
+            if g is None:
+                continue
+            st = self.state.get(p, {})
+            if "exp_avg" not in st:
+                return None
+            sig.append((p.data_ptr(), g[0].data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()))
+        return tuple(sig)
+
+    def _build_table(self, group):
+        chunk = _lib.load().stcgan_adam_chunk()
+        entries, blocks, keep = [], [], []
+        for p in group["params"]:
+            gd = self._grad_of(p)
+            if gd is None:
+                continue
+            g, d0, d1 = gd
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()):
+                raise RuntimeError("FusedAdam handles contiguous float32 CUDA parameters/gradients only (no CPU path)")
+            st = self._state_for(p)
+            for k in ("exp_avg", "exp_avg_sq"):
+                if st[k].device != p.device or not st[k].is_contiguous():
+                    st[k] = st[k].to(p.device).contiguous()
+            ti = len(entries)
+            entries.append(_lib.AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                           st["exp_avg_sq"].data_ptr(), p.numel(), d0, d1))
+            keep.append((p, g, st))
+            blocks += [(ti, c) for c in range((p.numel() + chunk - 1) // chunk)]
+        if not entries:
+            return None
+        arr = (_lib.AdamTensor * len(entries))(*entries)
+        dev = keep[0][0].device
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        blk = torch.from_numpy(np.asarray(blocks, dtype=np.int32).reshape(-1).copy()).to(dev)
+        b1, b2 = group["betas"]
+        steps_done = float(keep[0][2]["step"].item())
+        hyper_host = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(self.grad_scale), steps_done, 0.0, 0.0]
+        hyper = torch.tensor(hyper_host, dtype=torch.float32, device=dev)
+        return dict(sig=self._signature(group), table=table, blocks=blk, nblocks=len(blocks), keep=keep,
+                    hyper=hyper, hyper_host=hyper_host)
+
+    def _sync_hyper(self, group, t):
+        """Push lr / grad_scale changes (ExponentialLR steps once per epoch, src/cgan.py:383-384) to the device."""
+        want = [float(group["lr"]), t["hyper_host"][1], t["hyper_host"][2], t["hyper_host"][3], float(self.grad_scale)]
+        if want != t["hyper_host"][:5]:
+            t["hyper_host"][:5] = want
+            t["hyper"][:5].copy_(torch.tensor(want, dtype=torch.float32), non_blocking=False)
+
+    def prepare(self):
+        """Build the device tables now (e.g. before CUDA-graph capture)."""
+        for gi, group in enumerate(self.param_groups):
+            t = self._tables.get(gi)
+            if t is None or t["sig"] != self._signature(group):
+                self._tables[gi] = self._build_table(group)
+
+    def bump_host_counters(self):
+        """Account on the host for one device-side step (used after a CUDA-graph replay of `step`)."""
+        for t in self._tables.values():
+            if t is not None:
+                for _, _, st in t["keep"]:
+                    st["step"] += 1
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        self.prepare()
+        for gi, group in enumerate(self.param_groups):
+            t = self._tables.get(gi)
+            if t is None:
+                continue
+            self._sync_hyper(group, t)
+            _lib.check(lib.stcgan_adam_step(t["table"].data_ptr(), t["blocks"].data_ptr(), t["nblocks"],
+                                            t["hyper"].data_ptr(), torch.cuda.current_stream().cuda_stream),
+                       "stcgan_adam_step")
+            for p, _, st in t["keep"]:
+                st["step"] += 1
+                torch.autograd.graph.increment_version(p)
+        return loss

@@ -1,0 +1,267 @@
+"""Per-kernel parity: every C-ABI kernel against the single torch op it replaces (CPU, float64 arbiter),
+fed IDENTICAL inputs (layer-local checks are where 1e-3 / 2e-2 are enforceable).
+
+fp32 mode (CUDA-core tiles)            : tolerance 1e-5 (north_star asks 1e-3)
+bf16 mode (tcgen05 / CUDA-core, bf16 IO): inputs are rounded to bf16 first, so the only error left is fp32
+                                         accumulation order + the bf16 rounding of the output: tol 6e-3
+                                         (north_star asks 2e-2)
+"""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 6e-3}
+
+
+def _nhwc(t, dtype, dev):
+    n, c, h, w = t.shape
+    out = torch.empty((n, h, w, c), dtype=dtype, device=dev)      # canonical strides even for size-1 dims
+    out.copy_(t.permute(0, 2, 3, 1))
+    return out
+
+
+def _nchw(t):
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def _round(t, mode):
+    return t.to(torch.bfloat16).float() if mode == "bf16" else t
+
+
+def _convop(kind, cin, cout, mode, dev, bias=False, seed=0):
+    from stcgan_b200 import nets, ops
+    g = torch.Generator().manual_seed(seed)
+    shape = (cin, cout, 4, 4) if kind == "convT" else (cout, cin, 4, 4)
+    w = torch.randn(shape, generator=g) * (1.0 / (16 * cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    wp = torch.nn.Parameter(w.to(dev))
+    bp = None if b is None else torch.nn.Parameter(b.to(dev))
+    op = nets.ConvOp(kind, wp, bp)
+    op.ensure_packed(ops.DTYPES[mode][1])
+    op.g = torch.zeros(16 * op.d0 * op.d1, dtype=torch.float32, device=dev)
+    op.gb = None if b is None else torch.zeros(cout, dtype=torch.float32, device=dev)
+    return op, w, b
+
+
+def _ref_forward(kind, x, w, b):
+    if kind == "conv2":
+        return F.conv2d(x, w, b, 2, 1)
+    if kind == "conv1":
+        return F.conv2d(x, w, b, 1, 1)
+    return F.conv_transpose2d(x, w, b, 2, 1)
+
+
+CASES = [
+    # kind, cin, cout, n, h, w
+    ("conv2", 64, 128, 2, 32, 32),     # e2-like (TC eligible)
+    ("conv2", 128, 64, 3, 16, 24),     # BN=64 tile, non-square
+    ("conv2", 64, 64, 2, 18, 14),      # small / ragged tiles
+    ("conv2", 512, 512, 4, 2, 2),      # e8-like: 1x1 output
+    ("conv2", 3, 64, 2, 32, 32),       # e1-like thin K (CUDA-core path in both modes)
+    ("conv2", 7, 64, 1, 20, 28),       # D c1-like
+    ("conv1", 256, 512, 2, 8, 8),      # D c4-like stride 1 (7x7 out)
+    ("conv1", 128, 128, 1, 32, 32),    # 31x31 out like D c4 at 256^2
+    ("conv1", 512, 1, 2, 9, 9),        # D c5-like thin N
+    ("convT", 128, 64, 2, 16, 16),     # decoder-like
+    ("convT", 1024, 512, 2, 2, 2),     # d7-like
+    ("convT", 512, 512, 4, 1, 1),      # d8-like: 1x1 input
+    ("convT", 128, 3, 2, 16, 16),      # d1-like thin N
+    ("convT", 64, 128, 1, 5, 7),       # odd input grid
+]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_forward_dgrad_wgrad(cuda, lib, mode, case):
+    from stcgan_b200 import ops
+    kind, cin, cout, n, h, w_ = case
+    dt = ops.DTYPES[mode][1]
+    op, w, b = _convop(kind, cin, cout, mode, cuda, bias=(cout <= 64))
+    g = torch.Generator().manual_seed(1)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), mode)
+    wr = _round(w, mode)
+    xd = x.double().requires_grad_(True)
+    wd = wr.double().requires_grad_(True)
+    ref = _ref_forward(kind, xd, wd, None if b is None else b.double())
+    oh, ow = ref.shape[2:]
+    assert (oh, ow) == op.out_size(h, w_)
+    out = op.forward(_nhwc(x, dt, cuda), oh, ow)
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(out), ref) < TOL[mode], "forward"
+    # backward with a random output gradient
+    go = _round(torch.randn(ref.shape, generator=g), mode)
+    ref.backward(go.double())
+    gx = op.dgrad(_nhwc(go, dt, cuda), h, w_)
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(gx), xd.grad) < TOL[mode], "dgrad"
+    op.wgrad(_nhwc(x, dt, cuda), _nhwc(go, dt, cuda))
+    gw = ops.unpack_grad(op.g, op.d0, op.d1)
+    torch.cuda.synchronize()
+    assert rel_err(gw, wd.grad) < (1e-5 if mode == "fp32" else 2e-5), "wgrad (fp32 accumulation of exact bf16 products)"
+    if b is not None:
+        assert rel_err(op.gb, go.double().sum(dim=(0, 2, 3))) < 1e-5, "bias grad"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_conv_reads_padding_out_of_range_and_writes_channel_slices(cuda, lib, mode):
+    """odd-size F.pad (stcgan_g.py:126-132) as out-of-range reads; in-place concat via channel-slice outputs."""
+    from stcgan_b200 import ops
+    dt = ops.DTYPES[mode][1]
+    op, w, _ = _convop("conv2", 64, 64, mode, cuda)
+    g = torch.Generator().manual_seed(3)
+    x = _round(torch.randn(2, 64, 15, 5, generator=g), mode)        # 15x5 -> padded 16x6 -> 8x3
+    ref = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), _round(w, mode).double(), None, 2, 1)
+    buf = torch.zeros(2, 8, 3, 192, dtype=dt, device=cuda)
+    op.forward(_nhwc(x, dt, cuda), 8, 3, out=buf[..., 64:128])
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(buf[..., 64:128]), ref) < TOL[mode]
+    assert float(buf[..., :64].abs().max()) == 0 and float(buf[..., 128:].abs().max()) == 0
+
+
+def test_pack_weight_layout(cuda, lib):
+    from stcgan_b200 import ops
+    w = torch.randn(24, 40, 4, 4)
+    for dt in (torch.float32, torch.bfloat16):
+        p1 = torch.empty(16, 24, 40, dtype=dt, device=cuda); p2 = torch.empty(16, 40, 24, dtype=dt, device=cuda)
+        ops.pack_weight(w.to(cuda), p1, p2)
+        r1 = w.permute(2, 3, 0, 1).reshape(16, 24, 40).to(dt); r2 = w.permute(2, 3, 1, 0).reshape(16, 40, 24).to(dt)
+        assert torch.equal(p1.cpu(), r1) and torch.equal(p2.cpu(), r2)
+    g = torch.randn(16, 24, 40, device=cuda)
+    assert torch.equal(ops.unpack_grad(g.reshape(-1), 24, 40).cpu(), g.cpu().permute(1, 2, 0).reshape(24, 40, 4, 4))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 9, 7, 64), (16, 4, 4, 512), (1, 2, 2, 8), (3, 31, 31, 128)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_act_forward_backward(cuda, lib, mode, shape, training):
+    """BN(train/eval) + LeakyReLU and ReLU dual output, with a crop, against torch ops in float64."""
+    from stcgan_b200 import nets, ops
+    from stcgan_b200._lib import ACT_LEAKY, ACT_RELU
+    dt = ops.DTYPES[mode][1]
+    n, h, w, c = shape
+    hc, wc = max(h - 1, 1), max(w - 1, 1)
+    g = torch.Generator().manual_seed(5)
+    bn = torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(c, generator=g) * 0.5 + 1); bn.bias.copy_(torch.randn(c, generator=g) * 0.2)
+        bn.running_mean.copy_(torch.randn(c, generator=g) * 0.1); bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    ref_bn = torch.nn.BatchNorm2d(c).double(); ref_bn.load_state_dict(bn.state_dict()); ref_bn.train(training)
+    bn = bn.to(cuda).train(training)
+    y = _round(torch.randn(n, c, h, w, generator=g) * 2 + 0.5, mode)
+    yd = y.double().requires_grad_(True)
+    z = ref_bn(yd)[:, :, :hc, :wc]
+    r1, r2 = F.leaky_relu(z, 0.2), F.relu(z)
+    op = nets.BNOp(bn)
+    op.ggamma = torch.zeros(c, device=cuda); op.gbeta = torch.zeros(c, device=cuda)
+    sc = nets._bn_scratch(c, cuda)
+    yk = _nhwc(y, dt, cuda)
+    o1 = torch.empty(n, hc, wc, c, dtype=dt, device=cuda); o2 = torch.empty_like(o1)
+    op.forward(yk, sc, training, o1, ACT_LEAKY, o2, ACT_RELU)
+    torch.cuda.synchronize()
+    tol = 1e-5 if mode == "fp32" else 6e-3
+    assert rel_err(_nchw(o1), r1) < tol and rel_err(_nchw(o2), r2) < tol
+    if training:
+        assert rel_err(bn.running_mean, ref_bn.running_mean) < 1e-5 and rel_err(bn.running_var, ref_bn.running_var) < 1e-5
+        assert int(bn.num_batches_tracked) == 1
+    g1 = _round(torch.randn(r1.shape, generator=g), mode); g2 = _round(torch.randn(r2.shape, generator=g), mode)
+    (r1 * g1.double()).sum().backward(retain_graph=True); (r2 * g2.double()).sum().backward()
+    dy = torch.empty_like(yk)
+    op.backward(yk, sc, training, _nhwc(g1, dt, cuda), ACT_LEAKY, _nhwc(g2, dt, cuda), ACT_RELU, dy, True)
+    torch.cuda.synchronize()
+    # bf16 inputs near a gate (|z| ~ rounding) may flip it: compare with a loose norm-wise tolerance in bf16
+    assert rel_err(_nchw(dy), yd.grad) < (1e-4 if mode == "fp32" else 2e-2)
+    assert rel_err(op.ggamma, ref_bn.weight.grad) < (1e-4 if mode == "fp32" else 2e-2)
+    assert rel_err(op.gbeta, ref_bn.bias.grad) < (1e-4 if mode == "fp32" else 2e-2)
+
+
+def test_batchnorm_single_value_raises(cuda, lib):
+    from stcgan_b200 import nets
+    from stcgan_b200._lib import ACT_RELU
+    bn = torch.nn.BatchNorm2d(8).to(cuda).train()
+    y = torch.zeros(1, 1, 1, 8, device=cuda)
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        nets.BNOp(bn).forward(y, nets._bn_scratch(8, cuda), True, torch.empty_like(y), ACT_RELU)
+
+
+def test_fused_loss_against_reference_golden(cuda, lib, golden):
+    """every AdversarialLoss branch value + gradient vs fixtures produced by the reference's src/loss.py."""
+    from stcgan_b200 import AdversarialLoss, DataLoss
+    cr = torch.tensor(golden["adv"]["C_real"]).to(cuda); cf = torch.tensor(golden["adv"]["C_fake"]).to(cuda)
+    for ls, rel, avg, d in itertools.product((0, 1), repeat=4):
+        key = f"ls{ls}_rel{rel}_avg{avg}_D{d}"
+        a, b = cr.clone().requires_grad_(True), cf.clone().requires_grad_(True)
+        v = AdversarialLoss(ls=bool(ls), rel=bool(rel), avg=bool(avg)).to(cuda)(a, b, D_loss=bool(d))
+        v.backward()
+        assert abs(v.item() - float(golden["adv"][key])) < 1e-6 * max(1, abs(float(golden["adv"][key]))), key
+        for grad, name in ((a.grad, "dreal"), (b.grad, "dfake")):
+            ref = torch.tensor(golden["adv"][f"{key}/{name}"])
+            got = torch.zeros_like(ref) if grad is None else grad.cpu()
+            assert (got - ref).abs().max().item() < 1e-7, (key, name)
+    p = torch.randn(2, 3, 17, 19, device=cuda, requires_grad=True); t = torch.randn(2, 3, 17, 19, device=cuda)
+    t.view(-1)[::7] = p.detach().view(-1)[::7]      # exact ties: sign(0) = 0 like F.l1_loss
+    v = DataLoss()(p, t); v.backward()
+    pc = p.detach().cpu().double().requires_grad_(True)
+    rv = F.l1_loss(pc, t.cpu().double()); rv.backward()
+    assert abs(v.item() - rv.item()) < 1e-6 and (p.grad.cpu().double() - pc.grad).abs().max().item() < 1e-9
+
+
+def test_fused_adam_matches_torch_adam(cuda, lib):
+    """torch.optim.Adam semantics (betas (0.5, 0.999), eps 1e-8 -- src/cgan.py:85-90) over several steps,
+    with gradients in parameter layout and in packed [16][d0][d1] layout."""
+    from stcgan_b200 import FusedAdam, ops
+    g = torch.Generator().manual_seed(0)
+    shapes = [(8, 12, 4, 4), (5,), (16, 4, 4, 4), (3,)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    ref = [p.clone().double().requires_grad_(True) for p in ps]
+    mine = [torch.nn.Parameter(p.clone().to(cuda)) for p in ps]
+    o_ref = torch.optim.Adam(ref, lr=5e-4, betas=(0.5, 0.999))
+    o_mine = FusedAdam(mine, lr=5e-4, betas=(0.5, 0.999))
+    packed = {0: torch.zeros(16 * 8 * 12, device=cuda), 2: torch.zeros(16 * 16 * 4, device=cuda)}
+    o_mine.set_packed_grads({id(mine[i]): (packed[i], shapes[i][0], shapes[i][1]) for i in packed})
+    for step in range(4):
+        for i, (r, m) in enumerate(zip(ref, mine)):
+            gr = torch.randn(r.shape, generator=g)
+            r.grad = gr.double()
+            if i in packed:
+                packed[i].copy_(gr.permute(2, 3, 0, 1).reshape(-1))
+            else:
+                m.grad = gr.to(cuda)
+        if step == 2:
+            for grp in o_ref.param_groups + o_mine.param_groups:
+                grp["lr"] = 2e-4                              # ExponentialLR-style change between steps
+        o_ref.step(); o_mine.step()
+        for r, m in zip(ref, mine):
+            assert rel_err(m, r) < 2e-6, step
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 4
+
+
+def test_float2uint_bit_exact(cuda, lib, golden):
+    """integer contract: (clip(a,0,1)*255).astype(uint8) bit-exact against the reference's utils.float2uint."""
+    from stcgan_b200 import ops
+    v = torch.tensor(golden["f2u"]["inputs"]).to(cuda)
+    assert np.array_equal(ops.float2uint(v).cpu().numpy(), golden["f2u"]["outputs"])
+    pre = torch.tensor(golden["f2u"]["pre"]).reshape(2, 2, 32, 32).to(cuda)      # tanh-range values
+    exp = (np.clip(pre.cpu().numpy() * 0.5 + 0.5, 0, 1) * 255).astype(np.uint8).transpose(0, 2, 3, 1)
+    assert np.array_equal(ops.float2uint_hwc(pre).cpu().numpy(), exp)
+
+
+def test_layout_kernels(cuda, lib):
+    from stcgan_b200 import ops
+    a = torch.randn(2, 3, 9, 11, device=cuda); b = torch.randn(2, 1, 9, 11, device=cuda); c = torch.randn(2, 3, 9, 11, device=cuda)
+    for dt in (torch.float32, torch.bfloat16):
+        p = ops.pack_input([a, b, c], 8, dt)
+        ref = torch.cat([a, b, c, torch.zeros(2, 1, 9, 11, device=cuda)], 1).permute(0, 2, 3, 1).to(dt)
+        assert torch.equal(p, ref)
+        assert torch.equal(ops.nhwc_to_nchw(p), ref.float().permute(0, 3, 1, 2))
+        assert torch.equal(ops.nchw_to_nhwc(a, dt), a.permute(0, 2, 3, 1).to(dt))
+        g = torch.zeros(2, 3, 9, 11, device=cuda)
+        ops.unpack_input_grad(p, 4, 3, g, False); ops.unpack_input_grad(p, 4, 3, g, True)
+        assert torch.equal(g, 2 * c.to(dt).float())

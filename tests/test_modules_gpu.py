@@ -1,0 +1,167 @@
+"""Module-level parity: UnetGenerator / NLayerDiscriminator (stcgan_b200) against the oracle (which is pinned to
+the reference modules) on identical weights and ISTD-shaped inputs.
+
+Tolerances (north_star): fp32 mode 1e-3, bf16 mode 2e-2, norm-wise per tensor on OUTPUTS.  Gradients are
+checked layer-locally in test_kernels_gpu.py; here, end-to-end, they use the noise-aware criterion of SURVEY 4.1:
+against a FLOAT64 oracle, err <= max(tol, 2 x err(float32 oracle vs float64 oracle)), plus cosine similarity.
+"""
+import pytest
+import torch
+
+import stcgan_oracle as O
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = {"fp32": 1e-3, "bf16": 2e-2}
+
+
+def _cast_state(sd, dtype):
+    return {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+
+
+def _oracle_grads(kind, sd, x, dout, dtype, training=True):
+    sd = _cast_state(sd, dtype)
+    keys = O.trainable_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    xi = x.to(dtype).requires_grad_(True)
+    fn = O.generator_forward if kind == "G" else O.discriminator_forward
+    out = fn(sd, xi, training=training)
+    out.backward(dout.to(dtype))
+    return out.detach(), xi.grad, {k: sd[k].grad for k in keys}, sd
+
+
+def _cos(a, b):
+    a, b = a.double().reshape(-1).cpu(), b.double().reshape(-1).cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def states():
+    return O.build_all_states()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("net", ["G1", "G2", "D1", "D2"])
+def test_forward_backward_vs_oracle(cuda, lib, states, mode, net):
+    import stcgan_b200 as S
+    cin = {"G1": 3, "G2": 4, "D1": 4, "D2": 7}[net]
+    mod = (S.UnetGenerator(cin, 1 if net == "G1" else 3, precision=mode) if net[0] == "G"
+           else S.NLayerDiscriminator(cin, precision=mode))
+    mod.load_state_dict(states[net])
+    mod.to(cuda).train()
+    x, m, y = O.make_istd_batch(2, 256, 256)
+    inp = {"G1": x, "G2": torch.cat((x, m), 1), "D1": torch.cat((x, m), 1), "D2": torch.cat((x, m, y), 1)}[net]
+    xi = inp.to(cuda).requires_grad_(True)
+    out = mod(xi)
+    g = torch.Generator().manual_seed(9)
+    dout = torch.randn(out.shape, generator=g) / out.numel() ** 0.5
+    out.backward(dout.to(cuda))
+    torch.cuda.synchronize()
+    o64, dx64, g64, sd64 = _oracle_grads(net[0], states[net], inp, dout, torch.float64)
+    o32, dx32, g32, sd32 = _oracle_grads(net[0], states[net], inp, dout, torch.float32)
+    tol = OUT_TOL[mode]
+    assert rel_err(out, o64) < tol, f"output rel err {rel_err(out, o64):.3e}"
+    # BN buffers after one training forward
+    for k, v in mod.state_dict().items():
+        if "running" in k:
+            assert rel_err(v, sd64[k]) < tol, k
+        if "num_batches" in k:
+            assert int(v) == int(sd64[k]) == 1
+    worst = 0.0
+    for (k, p) in mod.named_parameters():
+        noise = rel_err(g32[k], g64[k])
+        e = rel_err(p.grad, g64[k])
+        worst = max(worst, e)
+        bound = max(tol, 2 * noise) if mode == "fp32" else 0.5
+        assert e < bound, f"{k}: grad rel err {e:.3e} (fp32-vs-fp64 oracle noise {noise:.3e})"
+        assert _cos(p.grad, g64[k]) > (0.9999 if mode == "fp32" else 0.85), k
+    e = rel_err(xi.grad, dx64)
+    assert e < (max(tol, 2 * rel_err(dx32, dx64)) if mode == "fp32" else 0.5), f"input grad {e:.3e}"
+    print(f"{net} {mode}: out {rel_err(out, o64):.2e}  worst param-grad {worst:.2e}  dx {e:.2e}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_eval_mode_gradients_are_tight(cuda, lib, states, mode):
+    """eval-mode BN at B=1 is gate-flip free (SURVEY 4.1 iii): tight end-to-end gradient parity."""
+    import stcgan_b200 as S
+    mod = S.UnetGenerator(3, 1, precision=mode)
+    mod.load_state_dict(states["G1"]); mod.to(cuda).eval()
+    x = O.make_istd_batch(1, 256, 256, seed=3)[0]
+    xi = x.to(cuda).requires_grad_(True)
+    out = mod(xi)
+    dout = torch.randn(out.shape, generator=torch.Generator().manual_seed(2)) / out.numel() ** 0.5
+    out.backward(dout.to(cuda))
+    o64, dx64, g64, _ = _oracle_grads("G", states["G1"], x, dout, torch.float64, training=False)
+    tol = 1e-3 if mode == "fp32" else 6e-2
+    assert rel_err(out, o64) < OUT_TOL[mode]
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad, g64[k]) < tol, (k, rel_err(p.grad, g64[k]))
+    assert rel_err(xi.grad, dx64) < tol
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_odd_sizes_train_and_native_istd_eval(cuda, lib, states, mode):
+    """odd H/W pad+crop path (stcgan_g.py:126-132): 384x320 in train mode (BN statistics include the padded
+    row/column), 480x640 in eval mode (the inference geometry of BASELINE config 4)."""
+    import stcgan_b200 as S
+    mod = S.UnetGenerator(3, 1, precision=mode)
+    mod.load_state_dict(states["G1"]); mod.to(cuda)
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 384, 320, generator=gen).clamp(-1, 1)
+    sd = _cast_state(states["G1"], torch.float64)
+    ref = O.generator_forward(sd, x.double(), training=True)
+    mod.train()
+    out = mod(x.to(cuda))
+    assert out.shape == ref.shape and rel_err(out, ref) < OUT_TOL[mode]
+    for k, v in mod.state_dict().items():
+        if "running" in k:
+            assert rel_err(v, sd[k]) < OUT_TOL[mode], k
+    mod.load_state_dict(states["G1"]); mod.eval()
+    x = O.make_istd_batch(1, 480, 640, seed=5)[0]
+    ref = O.generator_forward(_cast_state(states["G1"], torch.float64), x.double(), training=False)
+    with torch.no_grad():
+        out = mod(x.to(cuda))
+    assert out.shape == (1, 1, 480, 640) and rel_err(out, ref) < OUT_TOL[mode]
+
+
+def test_weights_init_regime_and_small_width(cuda, lib):
+    """`weights_init` (src/networks.py:19-30, BN gamma ~ N(0, 0.02)) and a non-default width (ngf=16: every layer on
+    the CUDA-core path or a 64-channel tensor-core tile), B=1."""
+    import stcgan_b200 as S
+    torch.manual_seed(1)
+    mod = S.get_generator("stcgan", in_channels=4, out_channels=3, ngf=16, drop_rate=0.05, no_conv_t=False,
+                          use_selu=False, activation="none")
+    mod.apply(S.weights_init)
+    sd = {k: v.clone() for k, v in mod.state_dict().items()}
+    x = torch.randn(1, 4, 256, 256, generator=torch.Generator().manual_seed(0)).clamp(-1, 1)
+    ref = O.generator_forward(_cast_state(sd, torch.float64), x.double(), training=True)
+    for mode in ("fp32", "bf16"):
+        mod.load_state_dict(sd); mod.set_precision(mode).to(cuda).train()
+        assert rel_err(mod(x.to(cuda)), ref) < OUT_TOL[mode], mode
+    d = S.get_discriminator("stcgan", in_channels=7, out_channels=3, ndf=16, use_selu=False, use_sigmoid=True)
+    d.apply(S.weights_init)
+    sd = {k: v.clone() for k, v in d.state_dict().items()}
+    xd = torch.randn(2, 7, 64, 96, generator=torch.Generator().manual_seed(0)).clamp(-1, 1)
+    ref = O.discriminator_forward(_cast_state(sd, torch.float64), xd.double(), training=True, use_sigmoid=True)
+    d.set_precision("fp32").to(cuda).train()
+    assert rel_err(d(xd.to(cuda)), ref) < 1e-3
+
+
+def test_state_dict_roundtrip_and_module_protocol(cuda, lib, states):
+    """what src/cgan.py does to the modules: .to, .train/.eval, .requires_grad_, state_dict save/load, class names."""
+    import stcgan_b200 as S
+    g = S.UnetGenerator(3, 1).to(cuda)
+    g.load_state_dict(states["G1"])
+    sd = g.state_dict()
+    assert list(sd.keys()) == list(states["G1"].keys()) and len(sd) == 82
+    assert all(torch.equal(sd[k].cpu(), states["G1"][k]) for k in sd)
+    assert type(g).__name__ == "UnetGenerator" and type(S.NLayerDiscriminator(4)).__name__ == "NLayerDiscriminator"
+    d = S.NLayerDiscriminator(4).to(cuda)
+    d.requires_grad_(False)
+    x = torch.randn(1, 4, 64, 64, device=cuda, requires_grad=True)
+    d(x).sum().backward()                     # frozen D: input gradient only (cgan.py:317-324)
+    assert x.grad is not None and all(p.grad is None for p in d.parameters())
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        g(torch.zeros(1, 3, 256, 256))
