@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""ST-CGAN hot-path benchmark (BASELINE.json metric: train images/sec at 256x256, 16 images per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|infer]
+
+One "step" = one full ST-CGAN train step (src/cgan.py:274-351, VisualLoss off): G1,G2 forward, D1,D2 forward x4
+each, both backward phases, two Adam updates, on one synthetic ISTD-shaped batch of 16 images per GPU.
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM (CUDA-graph replay);
+`e2e` = the same through the public API with HOST (pinned) inputs copied in and the losses read back every step.
+`--impl reference` times the CPU restatement of the reference (oracle port: the reference is pure Python/torch and
+cannot travel to the GPU box) on a bounded sample of the same workload, on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "shadow-removal-istd_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+BATCH_PER_GPU, H, W = 16, 256, 256
+METRIC = "stcgan_train_images_per_sec_256x256_b16_per_gpu"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(batch, steps, train=True):
+    """images/s of the CPU oracle (port of the reference path) on all host threads; bounded sample."""
+    import stcgan_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    states = O.build_all_states()
+    tr = O.OracleTrainer(states)
+    x, m, y = O.make_istd_batch(batch, H, W, seed=42)
+    tr.train_step(x, m, y) if train else tr.forward_only(x, m, y)          # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(x, m, y) if train else tr.forward_only(x, m, y)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample_batch = 4
+    steps = max(1, min(args.steps, 3))
+    rate, cores = cpu_oracle_rate(sample_batch, steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": 1e3 * sample_batch / rate, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ST-CGAN full train step 256x256 (cgan.py:274-351, VisualLoss off), CPU, fp32"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} train steps on {sample_batch} of the 16 images (oracle port of src/cgan.py:274-351 "
+                                   "on torch CPU ops; the reference is pure Python and does not travel to the GPU box)"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def instrumented_breakdown(eng, x, m, y):
+    """One eager step with CUDA events around every library call of the convolution family; returns per-family
+    (seconds, algorithmic flops) so that the roofline entry is measured live, on the launching stream."""
+    from stcgan_b200 import ops
+    from stcgan_b200._lib import BACKEND_TC
+    rec = []
+    orig_conv, orig_wgrad = ops.tapconv, ops.tapwgrad
+
+    def timed(fn, flops_of, name_of):
+        def wrapper(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            rec.append((name_of(*a, **k), flops_of(*a, **k), e0, e1))
+            return out
+        return wrapper
+
+    def conv_flops(geom, xx, wp, nout, oh, ow, **k):
+        n, _, _, kk = xx.shape
+        taps = 4 if geom == 3 else 16
+        pix = n * oh * ow
+        return 2.0 * pix * nout * kk * taps
+
+    def wgrad_flops(geom, s, l, g, **k):
+        n, sh, sw, d0 = s.shape
+        return 2.0 * n * sh * sw * d0 * l.shape[3] * 16
+
+    ops.tapconv = timed(orig_conv, conv_flops, lambda *a, **k: "conv_tc" if k.get("backend") == BACKEND_TC else "conv_ffma")
+    ops.tapwgrad = timed(orig_wgrad, wgrad_flops, lambda *a, **k: "wgrad_tc" if k.get("backend") == BACKEND_TC else "wgrad_ffma")
+    import stcgan_b200.nets as nets
+    try:
+        e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_all0.record()
+        eng.train_step(x, m, y)
+        e_all1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.tapconv, ops.tapwgrad = orig_conv, orig_wgrad
+    fam = {}
+    for name, fl, e0, e1 in rec:
+        t, f, c = fam.get(name, (0.0, 0.0, 0))
+        fam[name] = (t + e0.elapsed_time(e1) * 1e-3, f + fl, c + 1)
+    return fam, e_all0.elapsed_time(e_all1) * 1e-3
+
+
+def run_b200(args, rank, world, local_rank):
+    import stcgan_b200 as S
+    import stcgan_oracle as O
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    torch.manual_seed(O.REFERENCE_SEED)
+    nets = dict(G1=S.UnetGenerator(3, 1), G2=S.UnetGenerator(4, 3), D1=S.NLayerDiscriminator(4), D2=S.NLayerDiscriminator(7))
+    for n in nets.values():
+        n.to(dev).train()
+    eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"], S.TrainConfig(), process_group=pg)
+    xs, ms, ys = O.make_istd_batch(BATCH_PER_GPU, H, W, seed=42 + rank)       # distinct shard per rank
+    host = [t.contiguous().pin_memory() for t in (xs, ms, ys)]
+    x, m, y = (t.to(dev) for t in host)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.capture(x, m, y, warmup=max(args.warmup, 3))
+    launches_per_step = eng.graph_launches
+    for _ in range(max(args.warmup, 3)):
+        eng.replay()
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.replay()
+    e1.record()
+    barrier()
+    dt = e0.elapsed_time(e1) * 1e-3
+    # ---- end to end: pinned host inputs in, losses out, every step --------------------------------------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    loss_host = None
+    for _ in range(args.steps):
+        losses = eng.replay(host[0], host[1], host[2])          # H2D copies of x, m, y inside
+        loss_host = losses.cpu()                                  # D2H read of the step's losses (synchronises)
+    e3.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dt_e2e = e2.elapsed_time(e3) * 1e-3
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = t.tolist()
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    images = BATCH_PER_GPU * world * args.steps
+    value, e2e_value = images / dt, images / dt_e2e
+    flops_step = O.train_step_flops(H, W) * BATCH_PER_GPU
+    # ---- roofline of the dominant kernel family, timed live with CUDA events ---------------------------------------
+    fam, eager_s = instrumented_breakdown(eng, x, m, y)
+    tc_t = sum(v[0] for k, v in fam.items() if k.endswith("_tc"))
+    tc_f = sum(v[1] for k, v in fam.items() if k.endswith("_tc"))
+    tc_n = sum(v[2] for k, v in fam.items() if k.endswith("_tc"))
+    achieved = tc_f / tc_t / 1e12 if tc_t > 0 else 0.0
+    roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tf_sustained"], "traffic": None,
+            "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all tcgen05 conv launches of one train step)",
+            "launches": tc_n, "flops_per_step": tc_f, "seconds_per_step": tc_t, "peak_source": peaks["source"] + ", sustained bf16",
+            "families": {k: {"s": v[0], "flops": v[1], "launches": v[2]} for k, v in fam.items()},
+            "whole_step_tflops": flops_step / (dt / args.steps) / 1e12}
+    cpu_rate, cores = cpu_oracle_rate(2, 2) if world == 1 else (None, None)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ST-CGAN full train step 256x256, 16 images/GPU (BASELINE configs[1]; cgan.py:274-351, VisualLoss off, "
+                               "MSE adversarial loss as executed, Adam beta=(0.5,0.999)), bf16 activations/weights, fp32 master+Adam",
+                   "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}", "l2": "per-step working set (>2 GB of activations "
+                   "and weights) exceeds the 126 MB L2; no explicit flush", "cuda_graph": True,
+                   "algorithmic_gflop_per_image": O.train_step_flops(H, W) / 1e9},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
+                "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": 1e3 * dt_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks, "roofline": roof,
+        "losses_last_step": dict(zip(S.engine.SLOTS, [float(v) for v in loss_host[:6]])),
+    }
+    if cpu_rate is not None:
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": "2 train steps on 2 of the 16 images (oracle port of src/cgan.py:274-351, torch CPU fp32)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus and args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    run_b200(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

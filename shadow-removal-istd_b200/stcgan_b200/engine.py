@@ -70,13 +70,10 @@ class STCGANEngine:
         self.last = {}
 
     # ------------------------------------------------------------------------------------------
-    def _allreduce(self, names, async_op=False):
-        if self.world == 1:
-            return []
-        import torch.distributed as dist
-        return [dist.all_reduce(self.rt[n].flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op) for n in names]
-
-    def _step_impl(self, x, m, y):
+    def _step_segments(self, x, m, y):
+        """The train step as a generator: it yields the names of the networks whose flat gradient buffers must
+        be all-reduced before the next segment runs (data parallelism); each segment between two yields is pure
+        kernel launches and can be captured into a CUDA graph."""
         cfg, rt = self.cfg, self.rt
         kind = ops.KIND_BCE if cfg.ls else ops.KIND_MSE
         real, fake = 1.0, (-1.0 if cfg.ls else 0.0)
@@ -89,6 +86,7 @@ class STCGANEngine:
         c2r, w2r = rt["D2"].forward([x, m, y], True)
         yp, wg2 = rt["G2"].forward([x, mp], True)
         c2f, w2f = rt["D2"].forward([x, mp, yp], True)
+        self.last = dict(m_pred=mp, y_pred=yp)
         self.losses.zero_()
         d1r, d1f, d2r, d2f = newg(c1r), newg(c1f), newg(c2r), newg(c2f)
         ops.fused_loss([
@@ -100,7 +98,7 @@ class STCGANEngine:
         rt["D1"].backward(w1r, d1r, False); rt["D1"].backward(w1f, d1f, False)
         rt["D2"].backward(w2r, d2r, False); rt["D2"].backward(w2f, d2f, False)
         del w1r, w1f, w2r, w2f
-        self._allreduce(("D1", "D2"))
+        yield ("D1", "D2"), True                              # blocking: optim_D needs the reduced gradients
         self.optim_D.step()                                   # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
@@ -122,58 +120,80 @@ class STCGANEngine:
         di1 = rt["D1"].backward(w1f, d1f, True, param_grads=False)
         ops.unpack_input_grad(di1, 3, 1, dm, True)
         dig2 = rt["G2"].backward(wg2, dy, True)
-        pending = self._allreduce(("G2",), async_op=True)     # overlaps G1's backward
         ops.unpack_input_grad(dig2, 3, 1, dm, True)           # G2's input gradient, mask channel (cgan.py:286)
+        yield ("G2",), False                                  # async: overlaps G1's backward
         rt["G1"].backward(wg1, dm, False)
-        pending += self._allreduce(("G1",), async_op=True)
-        for wk in pending:
-            wk.wait()
+        yield ("G1",), True
         self.optim_G.step()                                   # cgan.py:351
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step
-        return mp, yp
+
+    def _reduce(self, names, blocking, pending):
+        if self.world > 1:
+            import torch.distributed as dist
+            for n in names:
+                pending.append(dist.all_reduce(self.rt[n].flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if blocking:
+            for wk in pending:
+                wk.wait()
+            pending.clear()
 
     # ------------------------------------------------------------------------------------------
     def train_step(self, x, m, y):
         """x [B,3,H,W], m [B,1,H,W], y [B,3,H,W]: float32 CUDA tensors in [-1,1].  Returns the device tensor of
-        losses (index with SLOTS); nothing is synchronised."""
+        losses (index with SLOTS); nothing is synchronised with the host."""
         for t in (x, m, y):
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise RuntimeError("train_step expects float32 CUDA tensors")
-        mp, yp = self._step_impl(x.contiguous(), m.contiguous(), y.contiguous())
-        self.last = dict(m_pred=mp, y_pred=yp)
+        pending = []
+        for names, blocking in self._step_segments(x.contiguous(), m.contiguous(), y.contiguous()):
+            self._reduce(names, blocking, pending)
         return self.losses
 
     def capture(self, x, m, y, warmup=3):
-        """Capture the train step into a CUDA graph for inputs of this shape (static buffers)."""
-        if self.world > 1:
-            raise RuntimeError("CUDA-graph capture is used for single-GPU steps; multi-GPU steps run eagerly")
-        self._static = tuple(t.clone() for t in (x, m, y))
+        """Capture the train step for inputs of this shape: one CUDA graph per segment (the gradient all-reduces
+        of the data-parallel path run between graphs, on NCCL's stream)."""
+        self._static = tuple(t.contiguous().clone() for t in (x, m, y))
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._step_impl(*self._static)
+                self.train_step(*self._static)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.optim_D.prepare(); self.optim_G.prepare()
-        g = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(g):
-            mp, yp = self._step_impl(*self._static)
+        gen = self._step_segments(*self._static)
+        self._graphs, pool, pending = [], None, []
+        while True:
+            g = torch.cuda.CUDAGraph()
+            req = None
+            with torch.cuda.graph(g, pool=pool):
+                try:
+                    req = next(gen)
+                except StopIteration:
+                    pass
+            pool = g.pool()
+            self._graphs.append((g, req))
+            if req is None:
+                break
+            self._reduce(req[0], req[1], pending)     # keep ranks in lock-step during capture as well
         self.graph_launches = _lib.launch_count() - before
-        self._graph = g
-        self.last = dict(m_pred=mp, y_pred=yp)
-        return g
+        self._graph = True
+        return self._graphs
 
     def replay(self, x=None, m=None, y=None):
         """Run the captured step (optionally on new inputs of the captured shape)."""
-        if self._graph is None:
+        if not self._graph:
             raise RuntimeError("call capture() first")
         for dst, src in zip(self._static, (x, m, y)):
             if src is not None:
                 dst.copy_(src, non_blocking=True)
-        self._graph.replay()
+        pending = []
+        for g, req in self._graphs:
+            g.replay()
+            if req is not None:
+                self._reduce(req[0], req[1], pending)
         self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
         return self.losses
 

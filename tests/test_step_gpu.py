@@ -106,7 +106,10 @@ def test_engine_matches_autograd_modules(cuda, lib, states):
         assert abs(La[k] - v.item()) <= 1e-4 * abs(v.item()) + 1e-7, (k, La[k], v.item())
     for n in a:
         for (k, p), q in zip(a[n].named_parameters(), b[n].parameters()):
-            assert (p - q).abs().max().item() <= 2.5e-4, (n, k)      # <= ~lr/2: same update up to atomics ordering
+            d = (p - q).abs()
+            lr = cfg.lr_G if n[0] == "G" else cfg.lr_D
+            # Adam's first step is lr*sign(g): noise-level gradients (atomics ordering) may flip by up to 2*lr
+            assert d.max().item() <= 2.02 * lr and (d > 0.1 * lr).float().mean().item() < 0.02, (n, k)
 
 
 def test_cuda_graph_replay_equals_eager(cuda, lib, states):
