@@ -106,6 +106,32 @@ int stcgan_tapwgrad(int geom, int dtype, int backend,
                     const void* L, int LH, int LW, int D1, int ldl,
                     float* G, void* stream);
 
+/* ---- thin layers on the tensor cores (bf16) --------------------------------------------------------
+ * The first / last layers (Cin in {3,4,7}: stcgan_g.py:85-86 outermost, stcgan_d.py:22-23; Cout in {1,3}:
+ * stcgan_g.py:93-95, stcgan_d.py:49-50) have one GEMM dimension below a tensor-core tile.  Three layouts keep them on
+ * tcgen05 without inflating HBM traffic:
+ *   thin N : N padded to 16 in the packed weights only (stcgan_pack_weight_pad16); output written straight to NCHW fp32
+ *            (bias + Tanh/Sigmoid fused) or to an 8-channel NHWC gradient tensor;
+ *   thin K : the thin tensor is kept zero-bordered with 8 channels, so one 4x4xC window is 4 rows of 64 contiguous
+ *            bytes; a 5-D TMA view turns it into two 128-byte K-chunks per output pixel (K = 128), weights packed
+ *            [n][(kh*4+kw)*8+c] (stcgan_pack_weight_thin);
+ *   thin wgrad : the same 5-D view as the M operand (128 = 16 taps x 8 channels), the fat tensor as N.
+ */
+int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp16,
+                          const float* bias, int act, void* y_nhwc8, int ldy, float* y_nchw_f32, int OH, int OW, int Nout,
+                          void* stream);
+/* out[n,oy,ox,:] = act(bias + sum_{kh,kw,c} t[n, stride*oy+kh, stride*ox+kw, c] * wthin[:, (kh*4+kw)*8+c]);
+ * t is zero-bordered [N, HP, WP, 8] bf16 (the border carries the conv padding), wthin [Nout][128] bf16 */
+int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
+                    void* y, int OH, int OW, int Nout, int ldy, void* stream);
+/* G += sum_q window(t, q)[(tap,c)] * f[q, d]; G index = [wtap][d][c] if fat_is_dim0 else [wtap][c][d] with
+ * wtap = flip ? 15 - tap : tap; t zero-bordered [N, HP, WP, 8] with thin_c real channels, f [N, FH, FW, Dfat] pitch ldf */
+int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_c, const void* f, int FH, int FW, int Dfat,
+                     int ldf, int fat_is_dim0, int flip, float* G, void* stream);
+/* thin weight packings from the torch parameter W[d0][d1][4][4] (fp32) to bf16 */
+int stcgan_pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, void* stream);
+int stcgan_pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, void* stream);
+
 /* ---- weight layout ---------------------------------------------------------------------------
  * torch parameter W[d0][d1][4][4] fp32  ->  P1[t][d0][d1] and P2[t][d1][d0] in `dtype`
  * (either output may be NULL).  State-dict layout: src/models/stcgan_g.py:85-109, stcgan_d.py:22-50. */
@@ -151,7 +177,9 @@ int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out
  * replaces the torch.cat of NCHW inputs (src/cgan.py:281-289, 321-324): up to three NCHW fp32 sources are
  * gathered into one NHWC tensor of Cpad >= c0+c1+c2 channels (extra channels zero). */
 int stcgan_pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
-                      int N, int H, int W, void* out, int Cpad, void* stream);
+                      int N, int H, int W, int border, void* out, int Cpad, void* stream);
+/* `border` > 0 writes a zero frame of that many pixels around every image: out is [N, H+2b, W+2b, Cpad].  The thin
+ * tensor-core kernels below read their 4x4 windows out of such zero-bordered 8-channel tensors. */
 /* gradient of the above for a channel range: grad_nchw[n, c, h, w] (+)= g[n,h,w, coff + c] , c < cn */
 int stcgan_unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn,
                              float* grad_nchw, int accumulate, void* stream);
@@ -160,7 +188,8 @@ int stcgan_nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, in
 int stcgan_nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, void* stream);
 /* g_nhwc = dout * (1 - out^2) (Tanh backward, stcgan_g.py:97) or dout*out*(1-out) (Sigmoid, stcgan_d.py:52-53), NCHW fp32 in */
 int stcgan_out_act_bwd(int dtype, int act, const float* out_nchw, const float* dout_nchw, int N, int H, int W, int C,
-                       void* g, int ldg, void* stream);
+                       int border, void* g, int ldg, void* stream);
+/* with border > 0, g is [N, H+2b, W+2b, ldg] zero-bordered and zero in channels >= C */
 
 /* ---- losses ---------------------------------------------------------------------------------------
  * replaces: AdversarialLoss.cal_loss (src/loss.py:79-84: ls==0 -> MSE, ls!=0 -> BCE-with-logits against a scalar

@@ -11,7 +11,11 @@ int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int
                   const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
 // tapconv_tc.cu
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
-               void* y, int Nout, int ldy, cudaStream_t st);
+               void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32);
+int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
+                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st);
+int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const void* f, int FH, int FW, int Dfat, int ldf,
+                 int fat_is_dim0, int flip, float* G, cudaStream_t st);
 int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
                 const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
 // bn_act.cu
@@ -32,12 +36,14 @@ int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cud
 int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, cudaStream_t st);
 int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cudaStream_t st);
 int pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
-               int N, int H, int W, void* out, int Cpad, cudaStream_t st);
+               int N, int H, int W, int border, void* out, int Cpad, cudaStream_t st);
+int pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, cudaStream_t st);
+int pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, cudaStream_t st);
 int unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn, float* grad,
                       int accumulate, cudaStream_t st);
 int nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, float* out, cudaStream_t st);
 int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* out, int ld, cudaStream_t st);
-int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, void* g, int ldg,
+int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, int border, void* g, int ldg,
                 cudaStream_t st);
 int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st);
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st);
@@ -77,7 +83,7 @@ int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int I
   if (N == 0) return 0;
   if (backend == STCGAN_BACKEND_TC) {
     if (dtype != STCGAN_BF16 || out_nchw_f32) return STCGAN_EUNSUPPORTED;
-    return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream));
+    return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream), 0, nullptr);
   }
   if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
   return tapconv_ffma(g, dtype, x, K, ldx, wp, bias, act, y, Nout, ldy, out_nchw_f32, as_stream(stream));
@@ -149,9 +155,44 @@ int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out
 }
 
 int stcgan_pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
-                      int N, int H, int W, void* out, int Cpad, void* stream) {
+                      int N, int H, int W, int border, void* out, int Cpad, void* stream) {
   STCGAN_REQUIRE(dtype_ok(dtype) && out && (c0 == 0 || s0) && (c1 == 0 || s1) && (c2 == 0 || s2));
-  return pack_input(dtype, s0, c0, s1, c1, s2, c2, N, H, W, out, Cpad, as_stream(stream));
+  return pack_input(dtype, s0, c0, s1, c1, s2, c2, N, H, W, border, out, Cpad, as_stream(stream));
+}
+
+int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp16,
+                          const float* bias, int act, void* y_nhwc8, int ldy, float* y_nchw_f32, int OH, int OW, int Nout,
+                          void* stream) {
+  STCGAN_REQUIRE(x && wp16 && (y_nhwc8 || y_nchw_f32) && N >= 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && K > 0 && ldx >= K);
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_SIGMOID);
+  Geom g;
+  if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
+  if (N == 0) return 0;
+  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32);
+}
+
+int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
+                    void* y, int OH, int OW, int Nout, int ldy, void* stream) {
+  STCGAN_REQUIRE(t && wthin && y && N >= 0 && HP >= 4 && WP >= 4 && (stride == 1 || stride == 2) && OH > 0 && OW > 0 && ldy >= Nout);
+  if (N == 0) return 0;
+  return thinconv_tc(t, N, HP, WP, stride, wthin, bias, act, y, OH, OW, Nout, ldy, as_stream(stream));
+}
+
+int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_c, const void* f, int FH, int FW, int Dfat,
+                     int ldf, int fat_is_dim0, int flip, float* G, void* stream) {
+  STCGAN_REQUIRE(t && f && G && N >= 0 && HP >= 4 && WP >= 4 && (stride == 1 || stride == 2) && FH > 0 && FW > 0 && ldf >= Dfat);
+  if (N == 0) return 0;
+  return thinwgrad_tc(t, N, HP, WP, stride, thin_c, f, FH, FW, Dfat, ldf, fat_is_dim0, flip, G, as_stream(stream));
+}
+
+int stcgan_pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, void* stream) {
+  STCGAN_REQUIRE(w && out && D0 > 0 && D1 > 0);
+  return pack_weight_thin(w, D0, D1, n_is_d0, flip, out, as_stream(stream));
+}
+
+int stcgan_pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, void* stream) {
+  STCGAN_REQUIRE(w && out && D0 > 0 && D1 > 0);
+  return pack_weight_pad16(w, D0, D1, n_is_d0, out, as_stream(stream));
 }
 
 int stcgan_unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, int coff, int cn,
@@ -171,9 +212,9 @@ int stcgan_nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, v
 }
 
 int stcgan_out_act_bwd(int dtype, int act, const float* out_nchw, const float* dout_nchw, int N, int H, int W, int C,
-                       void* g, int ldg, void* stream) {
-  STCGAN_REQUIRE(dtype_ok(dtype) && out_nchw && dout_nchw && g && ldg >= C);
-  return out_act_bwd(dtype, act, out_nchw, dout_nchw, N, H, W, C, g, ldg, as_stream(stream));
+                       int border, void* g, int ldg, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && out_nchw && dout_nchw && g && ldg >= C && border >= 0);
+  return out_act_bwd(dtype, act, out_nchw, dout_nchw, N, H, W, C, border, g, ldg, as_stream(stream));
 }
 
 int stcgan_fused_loss(const stcgan_loss_term* host_terms, int nterms, float* loss_out, void* stream) {

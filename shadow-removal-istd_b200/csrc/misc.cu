@@ -46,6 +46,54 @@ int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, c
   return finish_launch();
 }
 
+// thin packings for the tensor-core path of the thin layers (bf16 only):
+//   pack_weight_thin : Wt[n][(kh*4+kw)*8 + c] = W[..](n, c, tap')   with tap' = flip ? 15 - tap : tap, zero for c >= C
+//                      (n, c) = (d0, d1) if n_is_d0 else (d1, d0)
+//   pack_weight_pad16: Wp[t][r][k], r < 16 (zero rows for r >= Nn), (n, k) = (d0, d1) if n_is_d0 else (d1, d0)
+__global__ void __launch_bounds__(256)
+pack_weight_thin_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d0, int flip, __nv_bfloat16* __restrict__ out) {
+  const int Nn = n_is_d0 ? D0 : D1, C = n_is_d0 ? D1 : D0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nn * 128) return;
+  const int n = i / 128, col = i % 128, tap = col / 8, c = col % 8;
+  float v = 0.f;
+  if (c < C) {
+    const int st = flip ? 15 - tap : tap;
+    const int d0 = n_is_d0 ? n : c, d1 = n_is_d0 ? c : n;
+    v = w[((long long)d0 * D1 + d1) * 16 + st];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256)
+pack_weight_pad16_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d0, __nv_bfloat16* __restrict__ out) {
+  const int Nn = n_is_d0 ? D0 : D1, K = n_is_d0 ? D1 : D0;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16LL * 16 * K) return;
+  const int k = (int)(i % K), r = (int)((i / K) % 16), t = (int)(i / (16LL * K));
+  float v = 0.f;
+  if (r < Nn) {
+    const int d0 = n_is_d0 ? r : k, d1 = n_is_d0 ? k : r;
+    v = w[((long long)d0 * D1 + d1) * 16 + t];
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+int pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, cudaStream_t st) {
+  const int Nn = n_is_d0 ? D0 : D1, C = n_is_d0 ? D1 : D0;
+  if (C > 8 || Nn < 1) return STCGAN_EINVAL;
+  pack_weight_thin_kernel<<<(Nn * 128 + 255) / 256, 256, 0, st>>>(w, D0, D1, n_is_d0, flip, static_cast<__nv_bfloat16*>(out));
+  return finish_launch();
+}
+
+int pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, cudaStream_t st) {
+  const int Nn = n_is_d0 ? D0 : D1, K = n_is_d0 ? D1 : D0;
+  if (Nn > 16 || Nn < 1) return STCGAN_EINVAL;
+  const long long total = 16LL * 16 * K;
+  pack_weight_pad16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, D0, D1, n_is_d0, static_cast<__nv_bfloat16*>(out));
+  return finish_launch();
+}
+
 // G[t][d0][d1] -> grad[d0][d1][16]
 __global__ void __launch_bounds__(256)
 unpack_grad_kernel(const float* __restrict__ g, int D0, int D1, float* __restrict__ grad, int accumulate) {
@@ -81,29 +129,35 @@ int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cud
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
-                  const float* __restrict__ s2, int c2, int N, long long HW, T* __restrict__ out, int Cpad) {
-  const long long P = (long long)N * HW;
+                  const float* __restrict__ s2, int c2, int N, int H, int W, int border, T* __restrict__ out, int Cpad) {
+  const int HP = H + 2 * border, WP = W + 2 * border;
+  const long long HW = (long long)H * W, P = (long long)N * HP * WP;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-    const long long n = p / HW, r = p % HW;
+    const int xp = (int)(p % WP); const long long t = p / WP;
+    const int yp = (int)(t % HP); const long long n = t / HP;
+    const int yy = yp - border, xx = xp - border;
     T* o = out + p * Cpad;
     int c = 0;
-    for (int i = 0; i < c0; ++i) o[c++] = from_f32<T>(s0[(n * c0 + i) * HW + r]);
-    for (int i = 0; i < c1; ++i) o[c++] = from_f32<T>(s1[(n * c1 + i) * HW + r]);
-    for (int i = 0; i < c2; ++i) o[c++] = from_f32<T>(s2[(n * c2 + i) * HW + r]);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const long long r = (long long)yy * W + xx;
+      for (int i = 0; i < c0; ++i) o[c++] = from_f32<T>(s0[(n * c0 + i) * HW + r]);
+      for (int i = 0; i < c1; ++i) o[c++] = from_f32<T>(s1[(n * c1 + i) * HW + r]);
+      for (int i = 0; i < c2; ++i) o[c++] = from_f32<T>(s2[(n * c2 + i) * HW + r]);
+    }
     for (; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
   }
 }
 
 int pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
-               int N, int H, int W, void* out, int Cpad, cudaStream_t st) {
-  if (c0 + c1 + c2 > Cpad || c0 < 0 || c1 < 0 || c2 < 0) return STCGAN_EINVAL;
-  const long long HW = (long long)H * W, P = N * HW;
+               int N, int H, int W, int border, void* out, int Cpad, cudaStream_t st) {
+  if (c0 + c1 + c2 > Cpad || c0 < 0 || c1 < 0 || c2 < 0 || border < 0) return STCGAN_EINVAL;
+  const long long P = (long long)N * (H + 2 * border) * (W + 2 * border);
   if (P == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
   if (dtype == STCGAN_F32)
-    pack_input_kernel<float><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, HW, static_cast<float*>(out), Cpad);
+    pack_input_kernel<float><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, H, W, border, static_cast<float*>(out), Cpad);
   else
-    pack_input_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, HW,
+    pack_input_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, H, W, border,
                                                                   static_cast<__nv_bfloat16*>(out), Cpad);
   return finish_launch();
 }
@@ -189,27 +243,36 @@ int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* ou
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-out_act_bwd_kernel(int act, const float* __restrict__ o, const float* __restrict__ d, int N, long long HW, int C,
-                   T* __restrict__ g, int ldg) {
-  const long long P = (long long)N * HW;
+out_act_bwd_kernel(int act, const float* __restrict__ o, const float* __restrict__ d, int N, int H, int W, int C,
+                   int border, T* __restrict__ g, int ldg) {
+  const int HP = H + 2 * border, WP = W + 2 * border;
+  const long long HW = (long long)H * W, P = (long long)N * HP * WP;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-    const long long n = p / HW, r = p % HW;
-    for (int c = 0; c < C; ++c) {
-      const float ov = o[(n * C + c) * HW + r], dv = d[(n * C + c) * HW + r];
-      const float gv = act == STCGAN_ACT_TANH ? dv * (1.f - ov * ov)
-                     : act == STCGAN_ACT_SIGMOID ? dv * ov * (1.f - ov) : dv;
+    const int xp = (int)(p % WP); const long long t = p / WP;
+    const int yp = (int)(t % HP); const long long n = t / HP;
+    const int yy = yp - border, xx = xp - border;
+    const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const long long r = (long long)yy * W + xx;
+    for (int c = 0; c < ldg; ++c) {
+      float gv = 0.f;
+      if (in && c < C) {
+        const float ov = o[(n * C + c) * HW + r], dv = d[(n * C + c) * HW + r];
+        gv = act == STCGAN_ACT_TANH ? dv * (1.f - ov * ov) : act == STCGAN_ACT_SIGMOID ? dv * ov * (1.f - ov) : dv;
+      } else if (border == 0 && c >= C) {
+        continue;     // un-bordered mode keeps the historical contract: only the C real channels are written
+      }
       g[p * ldg + c] = from_f32<T>(gv);
     }
   }
 }
 
-int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, void* g, int ldg,
+int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, int border, void* g, int ldg,
                 cudaStream_t st) {
-  const long long HW = (long long)H * W, P = N * HW;
+  const long long P = (long long)N * (H + 2 * border) * (W + 2 * border);
   if (P == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  if (dtype == STCGAN_F32) out_act_bwd_kernel<float><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, HW, C, static_cast<float*>(g), ldg);
-  else out_act_bwd_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, HW, C, static_cast<__nv_bfloat16*>(g), ldg);
+  if (dtype == STCGAN_F32) out_act_bwd_kernel<float><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, H, W, C, border, static_cast<float*>(g), ldg);
+  else out_act_bwd_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, H, W, C, border, static_cast<__nv_bfloat16*>(g), ldg);
   return finish_launch();
 }
 

@@ -60,6 +60,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -97,6 +103,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -144,6 +160,11 @@ struct alignas(64) TapGemmParams {
   int Nout, ldy, act;
   const float* bias;
   __nv_bfloat16* y;
+  // thin variants
+  int thin_k;              // 1: A rows are im2col windows of a zero-bordered 8-channel tensor (5D map in amap[0]),
+                           //    K = 128 = two 64-wide chunks (kh pairs); ntaps = 1, kchunks = 2
+  int nout_real;           // BN == 16 only: number of valid output channels (<= 16)
+  float* y32;              // BN == 16 only: NCHW fp32 output (bias + activation incl. tanh / sigmoid) instead of y
 };
 
 template <int BN, int STAGES>
@@ -153,6 +174,7 @@ struct TapGemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
 template <int BN, int STAGES>
@@ -182,7 +204,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -198,7 +220,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
-      tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
+      if (P.thin_k)
+        tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, 2 * kc, b0, a0, n0);
+      else
+        tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
       tma_load_2d(&P.bmap, &full_bar[s], b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0);
     }
   } else if (threadIdx.x == 32) {
@@ -231,23 +256,47 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+    if constexpr (BN == 16) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16), r);
       if (valid) {
+        if (P.y32) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+          for (int co = 0; co < 16; ++co) {
+            if (co < P.nout_real) {
+              const float f = __uint_as_float(r[co]) + (P.bias ? P.bias[co] : 0.f);
+              P.y32[(((long long)n * P.nout_real + co) * P.OH + oy) * P.OW + ox] = act_fwd(P.act, f);
+            }
+          }
+        } else {   // 8-channel NHWC (gradient w.r.t. a packed thin input): one 16-byte store
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-            if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
-            f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
             w[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          *reinterpret_cast<uint4*>(out + c0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (valid) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+              if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
+              f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(out + c0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
     }
@@ -257,7 +306,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc<BN>(tmem_base);
+    tmem_dealloc<SM::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -273,6 +322,13 @@ struct alignas(64) WgradParams {
   int tiles_per_split;     // pixel tiles handled by one CTA (blockIdx.z = split)
   int D0, D1;
   float* G;
+  // thin mode: D[(tap,c)][d] = sum_q Twin[q,(tap,c)] * F[q,d] with T a zero-bordered 8-channel tensor (5D im2col map
+  // in lmap[0]) and F the fat tensor (smap).  M = 128 im2col columns, N = BN channels of F.
+  int thin;
+  int thin_c;              // real channels of T (<= 8)
+  int fat_is_dim0;         // F's channels index the weight's dim0 (else dim1)
+  int flip;                // window taps are the flipped kernel taps (stride-1 dgrad-style anchoring)
+  int Dfat;
 };
 
 template <int BN, int STAGES>
@@ -328,11 +384,19 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
-      tma_load_4d(&P.smap, &full_bar[s], a_dst, d0_0, b0, a0, n0);
-      tma_load_4d(&P.smap, &full_bar[s], a_dst + 8192, d0_0 + 64, b0, a0, n0);
+      if (P.thin) {
+        tma_load_5d(&P.lmap[0], &full_bar[s], a_dst, 0, 0, b0, a0, n0);          // kernel rows 0,1
+        tma_load_5d(&P.lmap[0], &full_bar[s], a_dst + 8192, 0, 2, b0, a0, n0);   // kernel rows 2,3
 #pragma unroll
-      for (int h = 0; h < BN / 64; ++h)
-        tma_load_4d(lm, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0 + P.tdx[tap], a0 + P.tdy[tap], n0);
+        for (int h = 0; h < BN / 64; ++h)
+          tma_load_4d(&P.smap, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0, a0, n0);
+      } else {
+        tma_load_4d(&P.smap, &full_bar[s], a_dst, d0_0, b0, a0, n0);
+        tma_load_4d(&P.smap, &full_bar[s], a_dst + 8192, d0_0 + 64, b0, a0, n0);
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h)
+          tma_load_4d(lm, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0 + P.tdx[tap], a0 + P.tdy[tap], n0);
+      }
     }
   } else if (threadIdx.x == 32) {
     constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);     // both operands MN-major
@@ -354,16 +418,34 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
     umma_commit(tmem_full);
   } else if (warp >= 2) {
     const int q = warp & 3;
-    const int d0 = d0_0 + q * 32 + lane;
-    float* out = P.G + ((long long)tap * P.D0 + d0) * P.D1 + d1_0;
+    const int row = q * 32 + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
+    if (P.thin) {
+      const int wtap = P.flip ? 15 - row / 8 : row / 8, c = row % 8;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (c < P.thin_c) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(out + c0 + e, __uint_as_float(r[e]));
+          for (int e = 0; e < 32; ++e) {
+            const int d = d1_0 + c0 + e;
+            const long long idx = P.fat_is_dim0 ? ((long long)wtap * P.Dfat + d) * P.thin_c + c
+                                                : ((long long)wtap * P.thin_c + c) * P.Dfat + d;
+            atomicAdd(P.G + idx, __uint_as_float(r[e]));
+          }
+        }
+      }
+    } else {
+      float* out = P.G + ((long long)tap * P.D0 + d0_0 + row) * P.D1 + d1_0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(out + c0 + e, __uint_as_float(r[e]));
+      }
     }
   }
 
@@ -453,13 +535,22 @@ static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
   return finish_launch();
 }
 
+// thin_n != 0: Nout <= 16 real output channels, wp packed with 16 (zero-padded) rows per tap; output goes to y32
+// (NCHW fp32, bias + any activation) or, if y32 == NULL, to the first 8 channels of an NHWC bf16 tensor.
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
-               void* y, int Nout, int ldy, cudaStream_t st) {
-  if (K % 64 != 0 || Nout % 64 != 0 || ldx % 8 != 0 || ldy % 8 != 0 || !al16(x) || !al16(y) || !al16(wp))
-    return STCGAN_EUNSUPPORTED;
-  if (act == STCGAN_ACT_TANH || act == STCGAN_ACT_SIGMOID) return STCGAN_EUNSUPPORTED;
+               void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr) {
+  if (K % 64 != 0 || ldx % 8 != 0 || !al16(x) || !al16(wp)) return STCGAN_EUNSUPPORTED;
+  if (!thin_n) {
+    if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(y)) return STCGAN_EUNSUPPORTED;
+    if (act == STCGAN_ACT_TANH || act == STCGAN_ACT_SIGMOID) return STCGAN_EUNSUPPORTED;
+  } else {
+    if (Nout > 16 || Nout < 1) return STCGAN_EUNSUPPORTED;
+    if (!y32 && (Nout > 8 || ldy % 8 != 0 || !al16(y) || bias || act != STCGAN_ACT_NONE)) return STCGAN_EUNSUPPORTED;
+  }
   TapGemmParams P;
   memset(&P, 0, sizeof(P));
+  P.nout_real = Nout; P.y32 = y32;
+  const int n_rows = thin_n ? 16 : Nout;     // rows per tap in the packed weight matrix
   int GH = 0, GW = 0;
   for (int c = 0; c < g.nclass; ++c) {
     if (g.grid_h(c) > GH) GH = g.grid_h(c);
@@ -491,7 +582,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
         if (rc) return rc;
       }
   }
-  rc = encode_2d(&P.bmap, wp, K, 16LL * Nout, Nout % 128 == 0 ? 128 : 64);
+  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (Nout % 128 == 0 ? 128 : 64));
   if (rc) return rc;
 
   for (int c = 0; c < g.nclass; ++c)
@@ -510,8 +601,56 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
       P.twt[c][j] = t.wtap;
     }
   (void)geom_kind;
+  P.Nout = n_rows;          // row pitch (per tap) of the packed weights
+  if (thin_n) {
+    dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), 1, (unsigned)g.nclass);
+    return launch_tapgemm<16, 5>(P, grid, st);
+  }
   const int BN = Nout % 128 == 0 ? 128 : 64;
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
+  if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
+  return launch_tapgemm<64, 4>(P, grid, st);
+}
+
+// 5D im2col view of a zero-bordered 8-channel tensor T [N, HP, WP, 8]:
+//   (d0 = (kw, c): 32 contiguous elements, d1 = kernel row kh (4), d2 = grid column, d3 = grid row, d4 = image)
+//   element address = ((n*HP + s*gy + kh)*WP + s*gx)*8 + d0       box = (32, 2, wt, ht, nt) -> [pixel][128 B]
+static int encode_thin5d(CUtensorMap* m, const void* base, long long HP, long long WP, long long N, int s,
+                         long long GW, long long GH, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  cuuint64_t dims[5] = {32, 4, (cuuint64_t)GW, (cuuint64_t)GH, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)WP * 16, (cuuint64_t)s * 16, (cuuint64_t)s * WP * 16, (cuuint64_t)HP * WP * 16};
+  cuuint32_t box[5] = {32, 2, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// thin-K convolution: out[p, n] = sum_{kh,kw,c} T[window(p)][kh][kw][c] * Wt[n][(kh*4+kw)*8 + c]
+//   T: zero-bordered [N, HP, WP, 8] bf16; output grid OH x OW with window anchor (s*oy, s*ox) in padded coordinates
+int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
+                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st) {
+  if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(t) || !al16(y) || !al16(wthin)) return STCGAN_EUNSUPPORTED;
+  if (act == STCGAN_ACT_TANH || act == STCGAN_ACT_SIGMOID) return STCGAN_EUNSUPPORTED;
+  if (s * (OH - 1) + 4 > HP || s * (OW - 1) + 4 > WP) return STCGAN_EINVAL;     // windows must stay inside the border
+  TapGemmParams P;
+  memset(&P, 0, sizeof(P));
+  choose_tile(TC_BM, OW, OH, N, &P.wt, &P.ht, &P.nt);
+  P.tiles_w = (OW + P.wt - 1) / P.wt; P.tiles_h = (OH + P.ht - 1) / P.ht;
+  const int tiles_n = (N + P.nt - 1) / P.nt;
+  P.GH = OH; P.GW = OW; P.N = N; P.OH = OH; P.OW = OW; P.ostride = 1;
+  P.ntaps = 1; P.kchunks = 2; P.thin_k = 1;
+  P.Nout = Nout; P.nout_real = Nout; P.ldy = ldy; P.act = act; P.bias = bias; P.y = static_cast<__nv_bfloat16*>(y);
+  int rc = encode_thin5d(&P.amap[0], t, HP, WP, N, s, OW, OH, P.wt, P.ht, P.nt);
+  if (rc) return rc;
+  for (int v = 1; v < 4; ++v) P.amap[v] = P.amap[0];
+  const int BN = Nout % 128 == 0 ? 128 : 64;
+  rc = encode_2d(&P.bmap, wthin, 128, Nout, BN);
+  if (rc) return rc;
+  dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), 1);
   if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
   return launch_tapgemm<64, 4>(P, grid, st);
 }
@@ -576,6 +715,36 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
       }
     }
   dim3 grid((unsigned)((D0 / 128) * (D1 / BN)), 16, (unsigned)splits);
+  if (BN == 128) return launch_wgrad<128, 4>(P, grid, st);
+  return launch_wgrad<64, 4>(P, grid, st);
+}
+
+// thin weight gradient: D[(tap,c)][d] = sum_q Twin[q,(tap,c)] * F[q,d]  ->  G (see WgradParams)
+//   T: zero-bordered [N, HP, WP, 8] bf16 with thin_c real channels; F: [N, FH, FW, Dfat] pitch ldf; the window of T
+//   for grid pixel q = (fy, fx) is anchored at (s*fy, s*fx) in padded coordinates.
+int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const void* f, int FH, int FW, int Dfat, int ldf,
+                 int fat_is_dim0, int flip, float* G, cudaStream_t st) {
+  if (Dfat % 64 != 0 || ldf % 8 != 0 || !al16(t) || !al16(f) || thin_c < 1 || thin_c > 8) return STCGAN_EUNSUPPORTED;
+  if (s * (FH - 1) + 4 > HP || s * (FW - 1) + 4 > WP) return STCGAN_EINVAL;
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  choose_tile(64, FW, FH, N, &P.wt, &P.ht, &P.nt);
+  P.tiles_w = (FW + P.wt - 1) / P.wt; P.tiles_h = (FH + P.ht - 1) / P.ht; P.tiles_n = (N + P.nt - 1) / P.nt;
+  P.thin = 1; P.thin_c = thin_c; P.fat_is_dim0 = fat_is_dim0; P.flip = flip; P.Dfat = Dfat;
+  P.D0 = 128; P.D1 = Dfat; P.G = G;
+  const int BN = Dfat % 128 == 0 ? 128 : 64;
+  const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+  const int out_tiles = Dfat / BN;
+  int splits = (2 * 148 + out_tiles - 1) / out_tiles;
+  if (splits > total_tiles) splits = total_tiles;
+  if (splits < 1) splits = 1;
+  P.tiles_per_split = (total_tiles + splits - 1) / splits;
+  splits = (total_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
+  int rc = encode_nhwc(&P.smap, f, Dfat, FW, FH, N, ldf, (long long)FW * ldf, (long long)FH * FW * ldf, P.wt, P.ht, P.nt);
+  if (rc) return rc;
+  rc = encode_thin5d(&P.lmap[0], t, HP, WP, N, s, FW, FH, P.wt, P.ht, P.nt);
+  if (rc) return rc;
+  dim3 grid((unsigned)out_tiles, 1, (unsigned)splits);
   if (BN == 128) return launch_wgrad<128, 4>(P, grid, st);
   return launch_wgrad<64, 4>(P, grid, st);
 }

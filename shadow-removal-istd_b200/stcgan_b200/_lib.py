@@ -57,11 +57,16 @@ SIGNATURES = {
     "stcgan_bn_act_bwd_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _i, _i,
                                      _p, _p, _i, _p, _p, _p]),
     "stcgan_colsum": (_i, [_i, _p, _i64, _i, _i, _p, _p]),
-    "stcgan_pack_input": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _i, _p]),
+    "stcgan_pack_input": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "stcgan_tapconv_thin_n": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "stcgan_thinconv": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "stcgan_thinwgrad": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "stcgan_pack_weight_thin": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "stcgan_pack_weight_pad16": (_i, [_p, _i, _i, _i, _p, _p]),
     "stcgan_unpack_input_grad": (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_nhwc_to_nchw": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "stcgan_nchw_to_nhwc": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p]),
-    "stcgan_out_act_bwd": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
+    "stcgan_out_act_bwd": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_fused_loss": (_i, [C.POINTER(LossTerm), _i, _p, _p]),
     "stcgan_adam_step": (_i, [_p, _p, _i, _p, _p]),
     "stcgan_adam_chunk": (_i, []),

@@ -37,6 +37,11 @@ class ConvOp:
         self.gb = None                    # bias gradient
         self.version = None
         self.use_tc = False
+        # thin layers on the tensor cores (bf16): "cin" = Conv2d with <= 8 input channels (first layers),
+        # "coutT" = ConvTranspose2d with <= 8 output channels (G's last layer), "cout1" = stride-1 Conv2d with <= 8
+        # output channels (D's last layer).  See include/stcgan_b200.h "thin layers".
+        self.thin = None
+        self.wthin = self.wp16 = None
 
     # ---- packing ------------------------------------------------------------------------
     def ensure_packed(self, act_dtype, force=False):
@@ -46,7 +51,30 @@ class ConvOp:
             if self.p1 is None or self.p1.dtype != act_dtype or self.p1.device != w.device:
                 self.p1 = torch.empty((16, self.d0, self.d1), dtype=act_dtype, device=w.device)
                 self.p2 = torch.empty((16, self.d1, self.d0), dtype=act_dtype, device=w.device)
-            ops.pack_weight(w.detach() if w.is_contiguous() else w.detach().contiguous(), self.p1, self.p2)
+            wc = w.detach() if w.is_contiguous() else w.detach().contiguous()
+            ops.pack_weight(wc, self.p1, self.p2)
+            self.thin = None
+            if act_dtype == torch.bfloat16:
+                if self.kind == "conv2" and self.cin <= 8 and self.cout % 64 == 0:
+                    self.thin = "cin"
+                elif self.kind == "convT" and self.cout <= 8 and self.cin % 64 == 0:
+                    self.thin = "coutT"
+                elif self.kind == "conv1" and self.cout <= 8 and self.cin % 64 == 0:
+                    self.thin = "cout1"
+            if self.thin is not None:
+                fat = self.cout if self.thin == "cin" else self.cin
+                if self.wthin is None or self.wthin.device != w.device:
+                    self.wthin = torch.empty((fat, 128), dtype=torch.bfloat16, device=w.device)
+                    self.wp16 = torch.empty((16, 16, fat), dtype=torch.bfloat16, device=w.device)
+                if self.thin == "cin":        # fwd: thin K over ci;  dgrad: thin N over ci
+                    ops.pack_weight_thin(wc, True, False, self.wthin)
+                    ops.pack_weight_pad16(wc, False, self.wp16)
+                elif self.thin == "coutT":    # fwd: thin N over co (= d1);  dgrad: thin K over co, rows ci (= d0)
+                    ops.pack_weight_pad16(wc, False, self.wp16)
+                    ops.pack_weight_thin(wc, True, False, self.wthin)
+                else:                         # fwd: thin N over co (= d0);  dgrad: thin K over co with flipped taps
+                    ops.pack_weight_pad16(wc, True, self.wp16)
+                    ops.pack_weight_thin(wc, False, True, self.wthin)
             self.version = ver
         self.use_tc = act_dtype == torch.bfloat16
 
@@ -61,22 +89,45 @@ class ConvOp:
             return ih - 1, iw - 1
         return ih * 2, iw * 2
 
-    def forward(self, x, oh, ow, *, out=None, out_nchw=None, act=ACT_NONE, use_bias=True):
+    def forward(self, x, oh, ow, *, out=None, out_nchw=None, act=ACT_NONE, use_bias=True, x_bordered=None):
         geom = {"conv2": GEOM_WIN_S2, "conv1": GEOM_WIN_S1, "convT": GEOM_PARITY}[self.kind]
         wp = self.p2 if self.kind == "convT" else self.p1
         bias = self.bias.detach() if (self.bias is not None and use_bias) else None
+        if self.thin == "cin" and x_bordered is not None and out_nchw is None:
+            return ops.thinconv(x_bordered, 2, self.wthin, self.cout, oh, ow, bias=bias, act=act, out=out)
+        if self.thin in ("coutT", "cout1") and out_nchw is not None:
+            ops.tapconv_thin_n(geom, x, self.wp16, self.cout, oh, ow, bias=bias, act=act, out_nchw=out_nchw)
+            return out_nchw
         plain = out_nchw is None and act in (ACT_NONE, ACT_LEAKY, ACT_RELU)
         return ops.tapconv(geom, x, wp, self.cout, oh, ow, bias=bias, act=act, out=out, out_nchw=out_nchw,
                            backend=self._backend_conv(self.cin, self.cout, plain))
 
-    def dgrad(self, g, ih, iw, *, out=None):
-        """gradient w.r.t. the layer input [N, ih, iw, cin] from g = gradient w.r.t. the layer output."""
+    def dgrad(self, g, ih, iw, *, out=None, out8=None, g_bordered=None):
+        """gradient w.r.t. the layer input [N, ih, iw, cin] from g = gradient w.r.t. the layer output.
+        Thin layers: `out8` = full 8-channel NHWC tensor for the thin-cin case; `g_bordered` = zero-bordered 8-channel
+        output gradient for the thin-cout cases."""
         geom = {"conv2": GEOM_PARITY, "conv1": GEOM_WIN_S1_FLIP, "convT": GEOM_WIN_S2}[self.kind]
         wp = self.p1 if self.kind == "convT" else self.p2
+        if self.thin == "cin" and out8 is not None:
+            ops.tapconv_thin_n(geom, g, self.wp16, self.cin, ih, iw, out8=out8)
+            return out8
+        if self.thin in ("coutT", "cout1") and g_bordered is not None:
+            return ops.thinconv(g_bordered, 2 if self.thin == "coutT" else 1, self.wthin, self.cin, ih, iw, out=out)
         return ops.tapconv(geom, g, wp, self.cin, ih, iw, out=out, backend=self._backend_conv(self.cout, self.cin))
 
-    def wgrad(self, x, g):
+    def wgrad(self, x, g, *, x_bordered=None, g_bordered=None):
         """accumulate the packed weight gradient from the layer input x and output gradient g."""
+        if self.thin == "cin" and x_bordered is not None:
+            ops.thinwgrad(x_bordered, 2, self.cin, g, self.g, True, False)
+            if self.bias is not None and self.gb is not None:
+                ops.colsum(g, self.gb)
+            return
+        if self.thin in ("coutT", "cout1") and g_bordered is not None:
+            ops.thinwgrad(g_bordered, 2 if self.thin == "coutT" else 1, self.cout, x, self.g,
+                          self.thin == "coutT", self.thin == "cout1")
+            if self.bias is not None and self.gb is not None:
+                ops.colsum(g_bordered[..., :self.cout], self.gb)
+            return
         if self.kind == "convT":
             s, l, geom = x, g, GEOM_WIN_S2
         else:
@@ -218,18 +269,24 @@ class GeneratorRuntime(_NetRuntimeBase):
         Returns (out NCHW fp32, workspace)."""
         self.ensure_packed()
         dt, dev, L = self.act_dtype, self.device(), self.L
-        inp = ops.pack_input(sources, self.cpad, dt)
-        n, h, w, _ = inp.shape
+        thin_in = self.downs[0].thin == "cin"
+        n, _, h, w = sources[0].shape
+        if thin_in:          # zero-bordered 8-channel input: the thin-K tensor-core path reads its windows from it
+            inp_b = ops.pack_input(sources, 8, dt, border=1)
+            inp = None
+        else:
+            inp_b = None
+            inp = ops.pack_input(sources, self.cpad, dt)
         s = self.sizes(h, w)
-        ws = {"inp": inp, "s": s, "training": training, "y": [None] * (L + 1), "a": [None] * (L + 1),
+        ws = {"inp": inp, "inp_b": inp_b, "n": n, "s": s, "training": training, "y": [None] * (L + 1), "a": [None] * (L + 1),
               "cat": [None] * (L + 1), "uy": [None] * (L + 2), "bn_d": [None] * (L + 1), "bn_u": [None] * (L + 2)}
         C = [None] + [d.cout for d in self.downs]
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
         # ---- encoder
-        x = inp[..., :self.cin]
+        x = None if thin_in else inp[..., :self.cin]
         for k in range(1, L + 1):
             hk, wk = s[k]
-            y = self.downs[k - 1].forward(x, hk, wk)
+            y = self.downs[k - 1].forward(x, hk, wk, x_bordered=inp_b if k == 1 else None)
             ws["y"][k] = y
             if k < L:
                 a = new(hk, wk, C[k])
@@ -269,15 +326,21 @@ class GeneratorRuntime(_NetRuntimeBase):
         returns the NHWC gradient of the packed input (or None)."""
         dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
         training = ws["training"]
-        n = ws["inp"].shape[0]
+        n = ws["n"]
         C = [None] + [d.cout for d in self.downs]
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
         # ---- outermost up conv (+Tanh)
-        g = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt)
         up = self.ups[0]
-        if param_grads:
-            up.wgrad(ws["cat"][1], g)
-        dcat = up.dgrad(g, *s[1])
+        if up.thin == "coutT":
+            g_b = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt, cpad=8, border=1)
+            if param_grads:
+                up.wgrad(ws["cat"][1], None, g_bordered=g_b)
+            dcat = up.dgrad(None, *s[1], g_bordered=g_b)
+        else:
+            g = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt)
+            if param_grads:
+                up.wgrad(ws["cat"][1], g)
+            dcat = up.dgrad(g, *s[1])
         # ---- decoder, outside-in
         for k in range(2, L + 1):
             up, bn, sc = self.ups[k - 1], self.up_bns[k - 1], ws["bn_u"][k]
@@ -305,14 +368,19 @@ class GeneratorRuntime(_NetRuntimeBase):
                 else:
                     ops.bn_act_bwd(y, None, None, None, training, da, ACT_LEAKY, skip_g, ACT_RELU, None, gy, None, None)
             down = self.downs[k - 1]
-            x_in = ws["a"][k - 1] if k > 1 else ws["inp"][..., :self.cin]
+            thin_in = k == 1 and ws["inp_b"] is not None
+            x_in = ws["a"][k - 1] if k > 1 else (None if thin_in else ws["inp"][..., :self.cin])
             if param_grads:
-                down.wgrad(x_in, gy)
+                down.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None)
             if k > 1:
                 da = down.dgrad(gy, *s[k - 1])
             elif need_input_grad:
-                dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
-                down.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                if thin_in:
+                    dinp = torch.empty((n, s[0][0], s[0][1], 8), dtype=dt, device=dev)
+                    down.dgrad(gy, *s[0], out8=dinp)
+                else:
+                    dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
+                    down.dgrad(gy, *s[0], out=dinp[..., :self.cin])
                 return dinp
         return None
 
@@ -332,11 +400,16 @@ class DiscriminatorRuntime(_NetRuntimeBase):
     def forward(self, sources, training):
         self.ensure_packed()
         dt, dev = self.act_dtype, self.device()
-        inp = ops.pack_input(sources, self.cpad, dt)
-        n, h, w, _ = inp.shape
+        thin_in = self.layers[0].thin == "cin"
+        n, _, h, w = sources[0].shape
+        if thin_in:
+            inp_b, inp = ops.pack_input(sources, 8, dt, border=1), None
+        else:
+            inp_b, inp = None, ops.pack_input(sources, self.cpad, dt)
         nl = len(self.layers)
-        ws = {"inp": inp, "training": training, "y": [None] * nl, "a": [None] * nl, "bn": [None] * nl, "s": [(h, w)]}
-        x = inp[..., :self.cin]
+        ws = {"inp": inp, "inp_b": inp_b, "n": n, "training": training, "y": [None] * nl, "a": [None] * nl,
+              "bn": [None] * nl, "s": [(h, w)]}
+        x = None if thin_in else inp[..., :self.cin]
         for i, conv in enumerate(self.layers):
             oh, ow = conv.out_size(*ws["s"][-1])
             if oh < 1 or ow < 1:
@@ -350,7 +423,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
             bn = self.layer_bns[i]
             if bn is None:
                 # bias + LeakyReLU fused into the conv epilogue; sign(a) == sign(pre-activation) serves the backward
-                a = conv.forward(x, oh, ow, act=ACT_LEAKY)
+                a = conv.forward(x, oh, ow, act=ACT_LEAKY, x_bordered=inp_b if i == 0 else None)
                 ws["a"][i] = a
             else:
                 y = conv.forward(x, oh, ow)
@@ -364,11 +437,19 @@ class DiscriminatorRuntime(_NetRuntimeBase):
         dt, dev = self.act_dtype, self.device()
         training, s = ws["training"], ws["s"]
         nl = len(self.layers)
-        n = ws["inp"].shape[0]
-        g = ops.out_act_bwd(ACT_SIGMOID if self.use_sigmoid else ACT_NONE, ws["out"], dout, dt)
+        n = ws["n"]
+        last = self.layers[nl - 1]
+        oact = ACT_SIGMOID if self.use_sigmoid else ACT_NONE
+        g_b = None
+        if last.thin == "cout1":
+            g_b = ops.out_act_bwd(oact, ws["out"], dout, dt, cpad=8, border=2)
+            g = None
+        else:
+            g = ops.out_act_bwd(oact, ws["out"], dout, dt)
         for i in range(nl - 1, -1, -1):
             conv = self.layers[i]
-            x_in = ws["a"][i - 1] if i > 0 else ws["inp"][..., :self.cin]
+            thin_in = i == 0 and ws["inp_b"] is not None
+            x_in = ws["a"][i - 1] if i > 0 else (None if thin_in else ws["inp"][..., :self.cin])
             if i < nl - 1:
                 bn = self.layer_bns[i]
                 if bn is None:
@@ -379,12 +460,21 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                     bn.backward(ws["y"][i], ws["bn"][i], training, g, ACT_LEAKY, None, ACT_NONE, gy, param_grads)
             else:
                 gy = g
+            if i == nl - 1 and g_b is not None:
+                if param_grads:
+                    conv.wgrad(x_in, None, g_bordered=g_b)
+                g = conv.dgrad(None, *s[i], g_bordered=g_b)
+                continue
             if param_grads:
-                conv.wgrad(x_in, gy)
+                conv.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None)
             if i > 0:
                 g = conv.dgrad(gy, *s[i])
             elif need_input_grad:
-                dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
-                conv.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                if thin_in:
+                    dinp = torch.empty((n, s[0][0], s[0][1], 8), dtype=dt, device=dev)
+                    conv.dgrad(gy, *s[0], out8=dinp)
+                else:
+                    dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
+                    conv.dgrad(gy, *s[0], out=dinp[..., :self.cin])
                 return dinp
         return None

@@ -169,22 +169,70 @@ def colsum(g, out):
     check(_lib.load().stcgan_colsum(_code(g), g.data_ptr(), n * h * w, c, ld, out.data_ptr(), _stream()), "stcgan_colsum")
 
 
-def pack_input(sources, cpad, dtype):
-    """NCHW fp32 sources (<= 3) -> one NHWC tensor with `cpad` channels (zero padded)."""
+def pack_input(sources, cpad, dtype, border=0):
+    """NCHW fp32 sources (<= 3) -> one NHWC tensor with `cpad` channels (zero padded) and an optional zero frame of
+    `border` pixels ([N, H+2b, W+2b, cpad])."""
     srcs = [s for s in sources]
     _need_cuda(*srcs)
     n, _, h, w = srcs[0].shape
     for s in srcs:
         assert s.dtype == torch.float32 and s.is_contiguous() and s.shape[0] == n and s.shape[2:] == (h, w)
-    out = torch.empty((n, h, w, cpad), dtype=dtype, device=srcs[0].device)
+    out = torch.empty((n, h + 2 * border, w + 2 * border, cpad), dtype=dtype, device=srcs[0].device)
     args = []
     for i in range(3):
         if i < len(srcs):
             args += [srcs[i].data_ptr(), srcs[i].shape[1]]
         else:
             args += [None, 0]
-    check(_lib.load().stcgan_pack_input(_code(out), *args, n, h, w, out.data_ptr(), cpad, _stream()), "stcgan_pack_input")
+    check(_lib.load().stcgan_pack_input(_code(out), *args, n, h, w, border, out.data_ptr(), cpad, _stream()), "stcgan_pack_input")
     return out
+
+
+def tapconv_thin_n(geom, x, wp16, nout, oh, ow, *, bias=None, act=ACT_NONE, out8=None, out_nchw=None):
+    """thin-N tap-GEMM on the tensor cores (nout <= 16): NCHW fp32 output (bias + activation) or an 8-channel NHWC one."""
+    n, ih, iw, k, ldx = _nhwc(x)
+    ldy = 0
+    if out8 is not None:
+        _, _, _, _, ldy = _nhwc(out8)
+    check(_lib.load().stcgan_tapconv_thin_n(geom, x.data_ptr(), n, ih, iw, k, ldx, wp16.data_ptr(),
+                                            None if bias is None else bias.data_ptr(), act,
+                                            None if out8 is None else out8.data_ptr(), ldy,
+                                            None if out_nchw is None else out_nchw.data_ptr(), oh, ow, nout, _stream()),
+          "stcgan_tapconv_thin_n")
+
+
+def thinconv(t, stride, wthin, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None):
+    """thin-K convolution of a zero-bordered 8-channel tensor t [N, HP, WP, 8] (tensor cores)."""
+    n, hp, wp_, c, _ = _nhwc(t)
+    assert c == 8 and t.is_contiguous() and t.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((n, oh, ow, nout), dtype=t.dtype, device=t.device)
+    _, _, _, _, ldy = _nhwc(out)
+    check(_lib.load().stcgan_thinconv(t.data_ptr(), n, hp, wp_, stride, wthin.data_ptr(),
+                                      None if bias is None else bias.data_ptr(), act, out.data_ptr(), oh, ow, nout, ldy,
+                                      _stream()), "stcgan_thinconv")
+    return out
+
+
+def thinwgrad(t, stride, thin_c, f, g, fat_is_dim0, flip):
+    """g (packed [16][d0][d1] fp32) += thin weight gradient from the zero-bordered thin tensor t and the fat tensor f."""
+    n, hp, wp_, c, _ = _nhwc(t)
+    n2, fh, fw, dfat, ldf = _nhwc(f)
+    assert c == 8 and n == n2 and t.is_contiguous() and g.numel() == 16 * dfat * thin_c
+    check(_lib.load().stcgan_thinwgrad(t.data_ptr(), n, hp, wp_, stride, thin_c, f.data_ptr(), fh, fw, dfat, ldf,
+                                       int(fat_is_dim0), int(flip), g.data_ptr(), _stream()), "stcgan_thinwgrad")
+
+
+def pack_weight_thin(w, n_is_d0, flip, out):
+    d0, d1 = w.shape[0], w.shape[1]
+    check(_lib.load().stcgan_pack_weight_thin(w.data_ptr(), d0, d1, int(n_is_d0), int(flip), out.data_ptr(), _stream()),
+          "stcgan_pack_weight_thin")
+
+
+def pack_weight_pad16(w, n_is_d0, out):
+    d0, d1 = w.shape[0], w.shape[1]
+    check(_lib.load().stcgan_pack_weight_pad16(w.data_ptr(), d0, d1, int(n_is_d0), out.data_ptr(), _stream()),
+          "stcgan_pack_weight_pad16")
 
 
 def unpack_input_grad(g, coff, cn, grad_nchw, accumulate):
@@ -209,13 +257,15 @@ def nchw_to_nhwc(x, dtype):
     return out
 
 
-def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None):
-    """gradient through the output activation, NCHW fp32 -> NHWC `dtype`."""
+def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None, border=0):
+    """gradient through the output activation, NCHW fp32 -> NHWC `dtype`; with `border`/`cpad` the result is the
+    zero-bordered, channel-padded layout [N, H+2b, W+2b, cpad] the thin tensor-core kernels read."""
     n, c, h, w = out_nchw.shape
     assert dout_nchw.is_contiguous() and out_nchw.is_contiguous() and dout_nchw.dtype == torch.float32
-    g = torch.empty((n, h, w, c), dtype=dtype, device=out_nchw.device)
-    check(_lib.load().stcgan_out_act_bwd(_code(g), act, out_nchw.data_ptr(), dout_nchw.data_ptr(), n, h, w, c,
-                                         g.data_ptr(), c, _stream()), "stcgan_out_act_bwd")
+    ld = c if cpad is None else cpad
+    g = torch.empty((n, h + 2 * border, w + 2 * border, ld), dtype=dtype, device=out_nchw.device)
+    check(_lib.load().stcgan_out_act_bwd(_code(g), act, out_nchw.data_ptr(), dout_nchw.data_ptr(), n, h, w, c, border,
+                                         g.data_ptr(), ld, _stream()), "stcgan_out_act_bwd")
     return g
 
 

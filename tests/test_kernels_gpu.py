@@ -265,3 +265,57 @@ def test_layout_kernels(cuda, lib):
         g = torch.zeros(2, 3, 9, 11, device=cuda)
         ops.unpack_input_grad(p, 4, 3, g, False); ops.unpack_input_grad(p, 4, 3, g, True)
         assert torch.equal(g, 2 * c.to(dt).float())
+
+
+THIN_CASES = [
+    # kind, cin, cout, n, h, w   (the thin first / last layers of G and D, on the tcgen05 thin paths in bf16 mode)
+    ("conv2", 3, 64, 2, 32, 32),      # G1 e1
+    ("conv2", 4, 64, 3, 16, 24),      # G2 e1 / D1 c1
+    ("conv2", 7, 64, 2, 20, 12),      # D2 c1 (+bias)
+    ("convT", 128, 1, 2, 16, 16),     # G1 d1 (+bias, tanh)
+    ("convT", 128, 3, 3, 8, 12),      # G2 d1
+    ("conv1", 512, 1, 2, 9, 9),       # D c5 (+bias)
+    ("conv1", 512, 1, 3, 31, 31),     # D c5 at the 256x256 geometry
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_thin_layers_on_tensor_cores(cuda, lib, case):
+    """thin-K (5-D im2col TMA view of a zero-bordered 8-channel tensor), thin-N (N padded to 16 in the weights only)
+    and thin wgrad kernels against the torch ops they replace, bf16 inputs, identical data."""
+    from stcgan_b200 import ops
+    from stcgan_b200._lib import ACT_NONE, ACT_TANH
+    kind, cin, cout, n, h, w_ = case
+    mode, dt = "bf16", torch.bfloat16
+    op, w, b = _convop(kind, cin, cout, mode, cuda, bias=True)
+    assert op.thin == {"conv2": "cin", "convT": "coutT", "conv1": "cout1"}[kind]
+    g = torch.Generator().manual_seed(2)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), mode)
+    xd = x.double().requires_grad_(True); wd = _round(w, mode).double().requires_grad_(True)
+    pre = _ref_forward(kind, xd, wd, b.double())
+    oh, ow = pre.shape[2:]
+    go = _round(torch.randn(pre.shape, generator=g), mode)
+    if kind == "conv2":
+        xb = ops.pack_input([x.to(cuda)], 8, dt, border=1)
+        out = op.forward(None, oh, ow, x_bordered=xb)
+        assert rel_err(_nchw(out), pre) < TOL[mode], "thin-K forward"
+        pre.backward(go.double())
+        d8 = torch.empty(n, h, w_, 8, dtype=dt, device=cuda)
+        op.dgrad(_nhwc(go, dt, cuda), h, w_, out8=d8)
+        assert rel_err(_nchw(d8[..., :cin]), xd.grad) < TOL[mode], "thin-N dgrad"
+        op.wgrad(None, _nhwc(go, dt, cuda), x_bordered=xb)
+        assert rel_err(op.gb, go.double().sum(dim=(0, 2, 3))) < 1e-5
+    else:
+        ref = torch.tanh(pre) if kind == "convT" else pre
+        out = torch.empty(n, cout, oh, ow, device=cuda)
+        op.forward(_nhwc(x, dt, cuda), oh, ow, out_nchw=out, act=ACT_TANH if kind == "convT" else ACT_NONE)
+        assert rel_err(out, ref) < 1e-5, "thin-N forward (fp32 NCHW output: no output rounding)"
+        pre.backward(go.double())
+        gb = ops.out_act_bwd(ACT_NONE, torch.zeros_like(go).to(cuda), go.to(cuda), dt, cpad=8, border=1 if kind == "convT" else 2)
+        gx = op.dgrad(None, h, w_, g_bordered=gb)
+        assert rel_err(_nchw(gx), xd.grad) < TOL[mode], "thin-K dgrad"
+        op.wgrad(_nhwc(x, dt, cuda), None, g_bordered=gb)
+        assert rel_err(op.gb, go.double().sum(dim=(0, 2, 3))) < 1e-5
+    gw = ops.unpack_grad(op.g, op.d0, op.d1)
+    torch.cuda.synchronize()
+    assert rel_err(gw, wd.grad) < 2e-5, "thin wgrad"
