@@ -124,13 +124,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 //   K-major operand  (rows of 64 bf16 = 128 B along K): SBO = 1024 B between 8-row groups, LBO unused (=1)
 //   MN-major operand (rows of 64 bf16 = 128 B along M/N, one row per K index): SBO = 1024 B between 8-K groups,
 //                     LBO = byte distance between consecutive 64-element M/N blocks
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// `layout`: 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows, 512-byte atoms)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M x N tile
@@ -220,9 +222,12 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
-      if (P.thin_k)
+      if (P.thin_k) {
+        // one 64-byte line per (pixel, kernel row): TMA gives every inner line its own swizzle-span row, so the two
+        // kernel rows of this K chunk are two separate [128 px][64 B] SWIZZLE_64B blocks
         tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, 2 * kc, b0, a0, n0);
-      else
+        tma_load_5d(&P.amap[0], &full_bar[s], a_dst + 8192, 0, 2 * kc + 1, b0, a0, n0);
+      } else
         tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
       tma_load_2d(&P.bmap, &full_bar[s], b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0);
     }
@@ -236,11 +241,20 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
       const uint32_t b_addr = a_addr + SM::A_BYTES;
+      if (P.thin_k) {
 #pragma unroll
-      for (int k = 0; k < TC_BK / 16; ++k) {
-        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-        umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+        for (int k = 0; k < 4; ++k) {   // block k/2 (kernel row), 16 K-elements k%2 inside its 64-byte rows
+          const uint64_t ad = make_smem_desc(a_addr + (k >> 1) * 8192 + (k & 1) * 32, 16, 512, 4);
+          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+        }
       }
       umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
     }
@@ -385,8 +399,9 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
       if (P.thin) {
-        tma_load_5d(&P.lmap[0], &full_bar[s], a_dst, 0, 0, b0, a0, n0);          // kernel rows 0,1
-        tma_load_5d(&P.lmap[0], &full_bar[s], a_dst + 8192, 0, 2, b0, a0, n0);   // kernel rows 2,3
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh)    // four [64 px][64 B] SWIZZLE_64B blocks: M rows (kh, kw, c)
+          tma_load_5d(&P.lmap[0], &full_bar[s], a_dst + kh * 4096, 0, kh, b0, a0, n0);
 #pragma unroll
         for (int h = 0; h < BN / 64; ++h)
           tma_load_4d(&P.smap, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0, a0, n0);
@@ -408,8 +423,9 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
       const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
       const uint32_t b_addr = a_addr + SM::A_BYTES;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {   // 64 pixels per stage = 4 x K16; 16 K-rows = 2048 B
-        const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);
+      for (int k = 0; k < 4; ++k) {   // 64 pixels per stage = 4 x K16; 16 K-rows = 2048 B (1024 B in 64-byte-row blocks)
+        const uint64_t ad = P.thin ? make_smem_desc(a_addr + k * 1024, 4096, 512, 4)
+                                   : make_smem_desc(a_addr + k * 2048, 8192, 1024);
         const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);
         umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
       }
@@ -614,17 +630,17 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
 
 // 5D im2col view of a zero-bordered 8-channel tensor T [N, HP, WP, 8]:
 //   (d0 = (kw, c): 32 contiguous elements, d1 = kernel row kh (4), d2 = grid column, d3 = grid row, d4 = image)
-//   element address = ((n*HP + s*gy + kh)*WP + s*gx)*8 + d0       box = (32, 2, wt, ht, nt) -> [pixel][128 B]
+//   element address = ((n*HP + s*gy + kh)*WP + s*gx)*8 + d0       box = (32, 1, wt, ht, nt) -> [pixel][64 B], SWIZZLE_64B
 static int encode_thin5d(CUtensorMap* m, const void* base, long long HP, long long WP, long long N, int s,
                          long long GW, long long GH, int bw, int bh, int bn) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
   cuuint64_t dims[5] = {32, 4, (cuuint64_t)GW, (cuuint64_t)GH, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)WP * 16, (cuuint64_t)s * 16, (cuuint64_t)s * WP * 16, (cuuint64_t)HP * WP * 16};
-  cuuint32_t box[5] = {32, 2, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
