@@ -108,12 +108,33 @@ def run_reference(args, rank):
 
 
 def instrumented_breakdown(eng, x, m, y):
-    """One eager step with CUDA events around every library call of the convolution family; returns per-family
-    (seconds, algorithmic flops) so that the roofline entry is measured live, on the launching stream."""
+    """One eager step with CUDA events around every launch of the convolution family; returns per-family
+    (seconds, algorithmic flops, launches).  A long device-side sleep is queued first so that the host runs ahead and the
+    event intervals contain kernel time only (measured live, on the launching stream)."""
     from stcgan_b200 import ops
     from stcgan_b200._lib import BACKEND_TC
     rec = []
-    orig_conv, orig_wgrad = ops.tapconv, ops.tapwgrad
+
+    def conv_flops(geom, xx, wp, nout, oh, ow, **k):
+        return 2.0 * xx.shape[0] * oh * ow * nout * xx.shape[3] * (4 if geom == 3 else 16)
+
+    def wgrad_flops(geom, s, l, g, **k):
+        return 2.0 * s.shape[0] * s.shape[1] * s.shape[2] * s.shape[3] * l.shape[3] * 16
+
+    def thinconv_flops(t, stride, wthin, nout, oh, ow, **k):
+        return 2.0 * t.shape[0] * oh * ow * nout * 128          # K padded to 16 taps x 8 channels
+
+    def thinwgrad_flops(t, stride, thin_c, f, g, *a, **k):
+        return 2.0 * f.shape[0] * f.shape[1] * f.shape[2] * f.shape[3] * 128
+
+    table = {
+        "tapconv": (conv_flops, lambda *a, **k: "conv_tc" if k.get("backend") == BACKEND_TC else "conv_ffma"),
+        "tapwgrad": (wgrad_flops, lambda *a, **k: "wgrad_tc" if k.get("backend") == BACKEND_TC else "wgrad_ffma"),
+        "tapconv_thin_n": (conv_flops, lambda *a, **k: "conv_tc_thin"),
+        "thinconv": (thinconv_flops, lambda *a, **k: "conv_tc_thin"),
+        "thinwgrad": (thinwgrad_flops, lambda *a, **k: "wgrad_tc_thin"),
+    }
+    saved = {}
 
     def timed(fn, flops_of, name_of):
         def wrapper(*a, **k):
@@ -125,27 +146,20 @@ def instrumented_breakdown(eng, x, m, y):
             return out
         return wrapper
 
-    def conv_flops(geom, xx, wp, nout, oh, ow, **k):
-        n, _, _, kk = xx.shape
-        taps = 4 if geom == 3 else 16
-        pix = n * oh * ow
-        return 2.0 * pix * nout * kk * taps
-
-    def wgrad_flops(geom, s, l, g, **k):
-        n, sh, sw, d0 = s.shape
-        return 2.0 * n * sh * sw * d0 * l.shape[3] * 16
-
-    ops.tapconv = timed(orig_conv, conv_flops, lambda *a, **k: "conv_tc" if k.get("backend") == BACKEND_TC else "conv_ffma")
-    ops.tapwgrad = timed(orig_wgrad, wgrad_flops, lambda *a, **k: "wgrad_tc" if k.get("backend") == BACKEND_TC else "wgrad_ffma")
-    import stcgan_b200.nets as nets
+    for name, (ff, nf) in table.items():
+        saved[name] = getattr(ops, name)
+        setattr(ops, name, timed(saved[name], ff, nf))
     try:
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(4e8))          # ~0.2 s of device time: the whole eager step queues up behind it
         e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_all0.record()
         eng.train_step(x, m, y)
         e_all1.record()
         torch.cuda.synchronize()
     finally:
-        ops.tapconv, ops.tapwgrad = orig_conv, orig_wgrad
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
     fam = {}
     for name, fl, e0, e1 in rec:
         t, f, c = fam.get(name, (0.0, 0.0, 0))
@@ -219,13 +233,14 @@ def run_b200(args, rank, world, local_rank):
     flops_step = O.train_step_flops(H, W) * BATCH_PER_GPU
     # ---- roofline of the dominant kernel family, timed live with CUDA events ---------------------------------------
     fam, eager_s = instrumented_breakdown(eng, x, m, y)
-    tc_t = sum(v[0] for k, v in fam.items() if k.endswith("_tc"))
-    tc_f = sum(v[1] for k, v in fam.items() if k.endswith("_tc"))
-    tc_n = sum(v[2] for k, v in fam.items() if k.endswith("_tc"))
+    tc_t = sum(v[0] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
+    tc_f = sum(v[1] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
+    tc_n = sum(v[2] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
     achieved = tc_f / tc_t / 1e12 if tc_t > 0 else 0.0
     roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tf_sustained"], "traffic": None,
-            "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all tcgen05 conv launches of one train step)",
+            "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all full-width tcgen05 conv launches of one train step)",
+            "eager_step_seconds": eager_s,
             "launches": tc_n, "flops_per_step": tc_f, "seconds_per_step": tc_t, "peak_source": peaks["source"] + ", sustained bf16",
             "families": {k: {"s": v[0], "flops": v[1], "launches": v[2]} for k, v in fam.items()},
             "whole_step_tflops": flops_step / (dt / args.steps) / 1e12}
