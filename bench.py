@@ -151,7 +151,7 @@ def instrumented_breakdown(eng, x, m, y):
         setattr(ops, name, timed(saved[name], ff, nf))
     try:
         torch.cuda.synchronize()
-        torch.cuda._sleep(int(4e8))          # ~0.2 s of device time: the whole eager step queues up behind it
+        torch.cuda._sleep(int(3e9))          # ~1.5 s of device time: the whole eager step queues up behind it
         e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_all0.record()
         eng.train_step(x, m, y)
