@@ -88,12 +88,14 @@ void stcgan_launch_count_reset(void);
  * act  : epilogue activation applied after bias
  * IH/IW may be smaller than the window reach implies: out-of-range taps read zeros, which is
  * also how the reference's odd-size F.pad (stcgan_g.py:126-132) is realised without a copy.
+ * workspace (optional, fp32, >= N*OH*OW*Nout*4 bytes): lets the tensor-core backend split the taps of deep-K layers with
+ * few output tiles (the U-Net bottleneck) over more CTAs; partial sums are reduced there in fp32.
  */
 int stcgan_tapconv(int geom, int dtype, int backend,
                    const void* x, int N, int IH, int IW, int K, int ldx,
                    const void* wp, const float* bias, int act,
                    void* y, int OH, int OW, int Nout, int ldy, int out_nchw_f32,
-                   void* stream);
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 /* weight gradient of the same convolutions:  G[t][d0][d1] += sum_p S[p, d0] * L[win_t(p), d1]
  * S : "small-grid" tensor [N, SH, SW, D0] pitch lds (Conv2d: dY; ConvTranspose2d: the layer input)

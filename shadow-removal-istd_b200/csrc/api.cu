@@ -11,7 +11,7 @@ int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int
                   const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
 // tapconv_tc.cu
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
-               void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32);
+               void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32, float* ws, long long ws_bytes);
 int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
                 void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st);
 int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const void* f, int FH, int FW, int Dfat, int ldf,
@@ -73,7 +73,7 @@ void stcgan_launch_count_reset(void) { g_launches = 0; }
 
 int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int IH, int IW, int K, int ldx,
                    const void* wp, const float* bias, int act, void* y, int OH, int OW, int Nout, int ldy,
-                   int out_nchw_f32, void* stream) {
+                   int out_nchw_f32, void* workspace, int64_t workspace_bytes, void* stream) {
   STCGAN_REQUIRE(dtype_ok(dtype) && x && wp && y);
   STCGAN_REQUIRE(N >= 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && K > 0 && Nout > 0 && ldx >= K);
   STCGAN_REQUIRE(out_nchw_f32 || ldy >= Nout);
@@ -83,7 +83,8 @@ int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int I
   if (N == 0) return 0;
   if (backend == STCGAN_BACKEND_TC) {
     if (dtype != STCGAN_BF16 || out_nchw_f32) return STCGAN_EUNSUPPORTED;
-    return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream), 0, nullptr);
+    return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream), 0, nullptr,
+                      static_cast<float*>(workspace), (long long)workspace_bytes);
   }
   if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
   return tapconv_ffma(g, dtype, x, K, ldx, wp, bias, act, y, Nout, ldy, out_nchw_f32, as_stream(stream));
@@ -168,7 +169,7 @@ int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K,
   Geom g;
   if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
   if (N == 0) return 0;
-  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32);
+  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32, nullptr, 0);
 }
 
 int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,

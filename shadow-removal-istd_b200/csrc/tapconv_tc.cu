@@ -117,6 +117,21 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// 16-byte vector reduction into global memory (sm_90+): one L2 transaction adds four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* addr, uint4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // descriptors
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +182,11 @@ struct alignas(64) TapGemmParams {
                            //    K = 128 = two 64-wide chunks (kh pairs); ntaps = 1, kchunks = 2
   int nout_real;           // BN == 16 only: number of valid output channels (<= 16)
   float* y32;              // BN == 16 only: NCHW fp32 output (bias + activation incl. tanh / sigmoid) instead of y
+  // split-K over taps (deep-K layers with few output tiles): blockIdx.z = class * ksplit + part; fp32 partial sums are
+  // reduced with vector red.global.add into `part_out` [N, OH, OW, Nout_total] (zeroed by the host wrapper)
+  int ksplit;
+  float* part_out;
+  int part_ld;
 };
 
 template <int BN, int STAGES>
@@ -191,13 +211,15 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z;
+  const int ksplit = P.ksplit > 1 ? P.ksplit : 1;
+  const int cls = blockIdx.z / ksplit, kpart = blockIdx.z % ksplit;
   const int n_col0 = blockIdx.y * BN;
   const int tw = blockIdx.x % P.tiles_w;
   const int th = (blockIdx.x / P.tiles_w) % P.tiles_h;
   const int tn = blockIdx.x / (P.tiles_w * P.tiles_h);
   const int b0 = tw * P.wt, a0 = th * P.ht, n0 = tn * P.nt;
-  const int iters = P.ntaps * P.kchunks;
+  const int taps_here = P.ntaps / ksplit, tap0 = kpart * taps_here;
+  const int iters = taps_here * P.kchunks;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&P.bmap);
@@ -218,7 +240,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      const int j = it / P.kchunks, kc = it % P.kchunks;
+      const int j = tap0 + it / P.kchunks, kc = it % P.kchunks;
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
@@ -292,26 +314,64 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
           *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-    } else {
+    } else if (P.part_out == nullptr) {
+      // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced
+      constexpr int PITCH = BN * 2 + 16;
+      const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if (valid) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint32_t w[4];
+        for (int v = 0; v < 4; ++v) {
+          uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-              if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
-              f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
-              const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-              w[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(out + c0 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; ++e) {
+            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+            if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
+            f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
+          st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
         }
+      }
+      __syncwarp();
+      constexpr int LPR = BN * 2 / 16;     // lanes per output row (16-byte pieces)
+      constexpr int RPI = 32 / LPR;        // rows per warp-wide store instruction
+      const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+      const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32) * PITCH;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += RPI) {
+        const int rr = i + lane / LPR;
+        const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+        if (pr) {
+          const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16);
+          *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+        }
+      }
+    } else {
+      // split-K partial: fp32 tile through smem, vector red.global.add of whole rows
+      constexpr int PITCH = BN * 4 + 16;
+      const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) st_shared_v4(stg + c0 * 4 + v * 16, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+      }
+      __syncwarp();
+      constexpr int LPR = BN * 4 / 16;     // 32 (BN=128) or 16 (BN=64)
+      constexpr int RPI = 32 / LPR;
+      float* po = P.part_out + ((long long)(n * P.OH + oy) * P.OW + ox) * P.part_ld + n_col0;
+      const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(po) : 0ull;
+      const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32) * PITCH;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += RPI) {
+        const int rr = i + lane / LPR;
+        const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+        if (pr) red_add_v4(reinterpret_cast<float*>(pr) + (lane % LPR) * 4, ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16));
       }
     }
   }
@@ -454,13 +514,26 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
         }
       }
     } else {
-      float* out = P.G + ((long long)tap * P.D0 + d0_0 + row) * P.D1 + d1_0;
+      // fp32 tile through (now idle) pipeline smem, then one vector red.global.add per 16 bytes of a whole row:
+      // a warp-wide instruction touches one or two contiguous rows instead of 32 different cache lines
+      constexpr int PITCH = BN * 4 + 16;
+      const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) atomicAdd(out + c0 + e, __uint_as_float(r[e]));
+        for (int v = 0; v < 8; ++v) st_shared_v4(stg + c0 * 4 + v * 16, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+      }
+      __syncwarp();
+      constexpr int LPR = BN * 4 / 16;
+      constexpr int RPI = 32 / LPR;
+      float* out = P.G + ((long long)tap * P.D0 + d0_0 + q * 32) * P.D1 + d1_0;
+      const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32) * PITCH;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += RPI) {
+        const int rr = i + lane / LPR;
+        red_add_v4(out + (long long)rr * P.D1 + (lane % LPR) * 4, ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16));
       }
     }
   }
@@ -553,8 +626,27 @@ static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
 
 // thin_n != 0: Nout <= 16 real output channels, wp packed with 16 (zero-padded) rows per tap; output goes to y32
 // (NCHW fp32, bias + any activation) or, if y32 == NULL, to the first 8 channels of an NHWC bf16 tensor.
+// fp32 split-K partial sums [P][Nout] -> bf16 y (pitch ldy) with bias + activation
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
+                     __nv_bfloat16* __restrict__ y, int ldy) {
+  const int quads = Nout / 4;
+  const long long total = P * quads;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / quads; const int c = (int)(i % quads) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
+    float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] = act_fwd(act, f[e] + (bias ? bias[c + e] : 0.f));
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
+  }
+}
+
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
-               void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr) {
+               void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr,
+               float* ws = nullptr, long long ws_bytes = 0) {
   if (K % 64 != 0 || ldx % 8 != 0 || !al16(x) || !al16(wp)) return STCGAN_EUNSUPPORTED;
   if (!thin_n) {
     if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(y)) return STCGAN_EUNSUPPORTED;
@@ -623,6 +715,24 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     return launch_tapgemm<16, 5>(P, grid, st);
   }
   const int BN = Nout % 128 == 0 ? 128 : 64;
+  // deep-K layers with few output tiles (the U-Net bottleneck): split the taps over extra CTAs, reduce in fp32
+  const long long ctas = (long long)P.tiles_w * P.tiles_h * tiles_n * (Nout / BN) * g.nclass;
+  const long long need = (long long)g.N * g.OH * g.OW * Nout * 4;
+  int ksplit = 1;
+  if (ws && ws_bytes >= need && ctas <= 74 && g.ntaps * P.kchunks >= 32)
+    while (ksplit * 2 <= g.ntaps && ctas * ksplit * 2 <= 296) ksplit *= 2;
+  if (ksplit > 1) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
+    if (e != cudaSuccess) return (int)e;
+    P.ksplit = ksplit; P.part_out = ws; P.part_ld = Nout;
+    dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)(g.nclass * ksplit));
+    rc = BN == 128 ? launch_tapgemm<128, 3>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
+    if (rc) return rc;
+    const long long Ppix = (long long)g.N * g.OH * g.OW;
+    long long blocks = (Ppix * (Nout / 4) + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
+    return finish_launch();
+  }
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
   if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
   return launch_tapgemm<64, 4>(P, grid, st);

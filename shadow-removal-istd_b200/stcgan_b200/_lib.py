@@ -46,7 +46,7 @@ SIGNATURES = {
     "stcgan_error_string": (C.c_char_p, [_i]),
     "stcgan_launch_count": (_i64, []),
     "stcgan_launch_count_reset": (None, []),
-    "stcgan_tapconv": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "stcgan_tapconv": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i64, _p]),
     "stcgan_tapwgrad": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight": (_i, [_i, _p, _i, _i, _p, _p, _p]),
     "stcgan_unpack_grad": (_i, [_p, _i, _i, _p, _i, _p]),

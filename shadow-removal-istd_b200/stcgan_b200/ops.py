@@ -54,6 +54,9 @@ def _nhwc(t: torch.Tensor):
     return n, h, w, c, ld
 
 
+SPLITK_MAX_ELEMS = 4 * 1024 * 1024     # only small outputs (bottleneck layers) get a split-K workspace
+
+
 def tc_eligible_conv(k: int, nout: int) -> bool:
     return k % 64 == 0 and nout % 64 == 0
 
@@ -76,9 +79,13 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
             out = torch.empty((n, oh, ow, nout), dtype=x.dtype, device=x.device)
         _, _, _, _, ldy = _nhwc(out)
         y, nchw = out, 0
+    ws, ws_bytes = None, 0
+    if backend == BACKEND_TC and n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
+        wst = torch.empty(n * oh * ow * nout, dtype=torch.float32, device=x.device)     # split-K partial sums
+        ws, ws_bytes = wst.data_ptr(), wst.numel() * 4
     check(lib.stcgan_tapconv(geom, _code(x), backend, x.data_ptr(), n, ih, iw, k, ldx, wp.data_ptr(),
                              None if bias is None else bias.data_ptr(), act, y.data_ptr(), oh, ow, nout, ldy, nchw,
-                             _stream()), "stcgan_tapconv")
+                             ws, ws_bytes, _stream()), "stcgan_tapconv")
     return y
 
 

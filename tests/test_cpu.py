@@ -125,9 +125,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_library_argument_validation_without_gpu(lib):
     """bad arguments are rejected on the host before any launch (error convention: negative code, no throw)."""
-    assert lib.stcgan_tapconv(99, 0, 0, 1, 1, 4, 4, 8, 8, 1, None, 0, 1, 2, 2, 8, 8, 0, None) == -1      # unknown geometry
-    assert lib.stcgan_tapconv(0, 7, 0, 1, 1, 4, 4, 8, 8, 1, None, 0, 1, 2, 2, 8, 8, 0, None) == -1       # unknown dtype
-    assert lib.stcgan_tapconv(0, 0, 1, 1, 1, 4, 4, 64, 64, 1, None, 0, 1, 2, 2, 64, 64, 0, None) == -2   # TC backend is bf16-only
+    assert lib.stcgan_tapconv(99, 0, 0, 1, 1, 4, 4, 8, 8, 1, None, 0, 1, 2, 2, 8, 8, 0, None, 0, None) == -1      # unknown geometry
+    assert lib.stcgan_tapconv(0, 7, 0, 1, 1, 4, 4, 8, 8, 1, None, 0, 1, 2, 2, 8, 8, 0, None, 0, None) == -1       # unknown dtype
+    assert lib.stcgan_tapconv(0, 0, 1, 1, 1, 4, 4, 64, 64, 1, None, 0, 1, 2, 2, 64, 64, 0, None, 0, None) == -2   # TC backend is bf16-only
     assert lib.stcgan_bn_stats(0, None, 10, 8, 8, None, None) == -1
     assert lib.stcgan_fused_loss(None, 1, None, None) == -1
     assert lib.stcgan_adam_chunk() == 4096
