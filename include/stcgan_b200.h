@@ -221,6 +221,8 @@ typedef struct stcgan_adam_tensor {
   float* p; const float* g; float* m; float* v;
   int64_t n;
   int32_t d0, d1;     /* packed-gradient dims, 0 = gradient in parameter layout */
+  void* p1; void* p2; /* optional (both or neither; needs d0 % 16 == 0 and d1 % 16 == 0): bf16 tap-major copies
+                         P1[t][d0][d1], P2[t][d1][d0] refreshed from the updated parameters in the same pass */
 } stcgan_adam_tensor;
 /* the table lives in DEVICE memory (built once); blocks[] maps each CUDA block to (tensor, chunk).
  * dev_hyper is a DEVICE array of 8 floats, in/out: {lr, beta1, beta2, eps, grad_scale, steps_done, -, -}.

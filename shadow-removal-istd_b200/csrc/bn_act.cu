@@ -72,10 +72,18 @@ bn_stats_kernel(const T* __restrict__ y, long long P, int C, int ld, double* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
     if (active) {
-      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
-        Vec8<T> v; v.load(y + p * ld + c0);
+      const long long stride = (long long)gridDim.x * rows;
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
+        Vec8<T> v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; q[i] = fmaf(v.v[i], v.v[i], q[i]); }
+        for (int u = 0; u < 4; ++u)            // issue all loads before using any: 64 B in flight per thread
+          if (p + u * stride < P) v[u].load(y + (p + u * stride) * ld + c0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (p + u * stride < P) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += v[u].v[i]; q[i] = fmaf(v[u].v[i], v[u].v[i], q[i]); }
+          }
       }
     }
     float* rs = red; float* rq = red + rows * cv * VEC;
@@ -163,19 +171,38 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = ss ? ss[c0 + i] : 1.f; sh[i] = ss ? ss[C + c0 + i] : 0.f; }
-    for (long long p = (long long)blockIdx.x * rows + tr; p < PC; p += (long long)gridDim.x * rows) {
-      const int w = (int)(p % WC); const long long t = p / WC;
-      const int h = (int)(t % HC); const long long n = t / HC;
-      Vec8<T> v; v.load(y + ((n * H + h) * W + w) * (long long)ldy + c0);
-      Vec8<T> a, b;
+    const long long stride = (long long)gridDim.x * rows;
+    const bool nocrop = HC == H && WC == W;
+    for (long long p0 = (long long)blockIdx.x * rows + tr; p0 < PC; p0 += 4 * stride) {
+      Vec8<T> v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = fmaf(v.v[i], sc[i], sh[i]);
-        a.v[i] = act_fwd(act1, z);
-        b.v[i] = act_fwd(act2, z);
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * stride;
+        if (p < PC) {
+          long long src = p;
+          if (!nocrop) {
+            const int w = (int)(p % WC); const long long t = p / WC;
+            const int h = (int)(t % HC); const long long n = t / HC;
+            src = (n * H + h) * W + w;
+          }
+          v[u].load(y + src * (long long)ldy + c0);
+        }
       }
-      a.store(o1 + p * ld1 + c0);
-      if (o2) b.store(o2 + p * ld2 + c0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * stride;
+        if (p < PC) {
+          Vec8<T> a, b;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v[u].v[i], sc[i], sh[i]);
+            a.v[i] = act_fwd(act1, z);
+            b.v[i] = act_fwd(act2, z);
+          }
+          a.store(o1 + p * ld1 + c0);
+          if (o2) b.store(o2 + p * ld2 + c0);
+        }
+      }
     }
   }
 }
@@ -183,33 +210,39 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+// raw operands of one pixel (8 channels): y, and the incoming gradients (zero outside the crop)
 template <typename T>
-__device__ __forceinline__ void load_dz(const T* y, int H, int W, int ldy, const float* sc, const float* sh,
-                                        const float* mean, const float* invstd, bool has_bn,
-                                        int HC, int WC, const T* g1, int ldg1, int act1,
-                                        const T* g2, int ldg2, int act2,
-                                        long long p, int c0, float* dz, float* xhat) {
-  // p indexes the FULL [N,H,W] grid
-  const int w = (int)(p % W); const long long t = p / W;
-  const int h = (int)(t % H); const long long n = t / H;
-  Vec8<T> v; v.load(y + p * ldy + c0);
-  const bool inside = h < HC && w < WC;
-  Vec8<T> a, b;
+struct BwdIn {
+  Vec8<T> y, a, b;
+  __device__ __forceinline__ void load(const T* yp, int H, int W, int ldy, int HC, int WC, const T* g1, int ldg1,
+                                       const T* g2, int ldg2, long long p, int c0) {
+    y.load(yp + p * ldy + c0);
+    long long pc = p;
+    bool inside = true;
+    if (HC != H || WC != W) {            // p indexes the FULL [N,H,W] grid; gradients live on the cropped grid
+      const int w = (int)(p % W); const long long t = p / W;
+      const int h = (int)(t % H); const long long n = t / H;
+      inside = h < HC && w < WC;
+      pc = (n * HC + h) * WC + w;
+    }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a.v[i] = 0.f; b.v[i] = 0.f; }
-  if (inside) {
-    const long long pc = (n * HC + h) * WC + w;
-    a.load(g1 + pc * ldg1 + c0);
-    if (g2) b.load(g2 + pc * ldg2 + c0);
+    for (int i = 0; i < 8; ++i) { a.v[i] = 0.f; b.v[i] = 0.f; }
+    if (inside) {
+      a.load(g1 + pc * ldg1 + c0);
+      if (g2) b.load(g2 + pc * ldg2 + c0);
+    }
   }
+  // dz = g1*act1'(z) + g2*act2'(z),  z = y*sc + sh
+  __device__ __forceinline__ void dz(const float* sc, const float* sh, int act1, int act2, bool two, float* out) const {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float z = has_bn ? fmaf(v.v[i], sc[i], sh[i]) : v.v[i];
-    dz[i] = a.v[i] * act_gate(act1, z) + (g2 ? b.v[i] * act_gate(act2, z) : 0.f);
-    xhat[i] = has_bn ? (v.v[i] - mean[i]) * invstd[i] : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(y.v[i], sc[i], sh[i]);
+      out[i] = a.v[i] * act_gate(act1, z) + (two ? b.v[i] * act_gate(act2, z) : 0.f);
+    }
   }
-}
+};
 
+// pass 1: acc[0][c] += sum dz ; acc[1][c] += sum dz * (y - mean)        (fp64 across threads / blocks)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
@@ -219,19 +252,26 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
   extern __shared__ float red[];
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool active = tr < rows;
+  const bool two = g2 != nullptr;
   for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
-    float sc[8], sh[8], mean[8], invstd[8], s[8], q[8];
+    float sc[8], sh[8], mean[8], s[8], q[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; invstd[i] = mi[C + c0 + i];
-      s[i] = 0.f; q[i] = 0.f;
-    }
+    for (int i = 0; i < 8; ++i) { sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; s[i] = 0.f; q[i] = 0.f; }
     if (active) {
-      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
-        float dz[8], xh[8];
-        load_dz<T>(y, H, W, ldy, sc, sh, mean, invstd, true, HC, WC, g1, ldg1, act1, g2, ldg2, act2, p, c0, dz, xh);
+      const long long stride = (long long)gridDim.x * rows;
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
+        BwdIn<T> in[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], xh[i], q[i]); }
+        for (int u = 0; u < 2; ++u)
+          if (p + u * stride < P) in[u].load(y, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (p + u * stride < P) {
+            float dz[8];
+            in[u].dz(sc, sh, act1, act2, two, dz);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], in[u].y.v[i] - mean[i], q[i]); }
+          }
       }
     }
     float* rs = red; float* rq = red + rows * cv * VEC;
@@ -251,6 +291,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
   }
 }
 
+// pass 2: dy = A*dz - B - (y - mean)*Cc  with A = gamma*invstd, B = A*mean(dz), Cc = A*invstd^2*mean(dz*(y-mean))
+//         (training);  dy = A*dz (eval);  dy = dz (no BatchNorm).  dgamma += invstd*acc[1], dbeta += acc[0].
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
@@ -261,35 +303,51 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int cv, int rows) {
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool has_bn = ss != nullptr;
+  const bool two = g2 != nullptr;
   if (has_bn && blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] += (float)acc[C + c];
+      dgamma[c] += (float)(acc[C + c] * (double)mi[C + c]);
       dbeta[c] += (float)acc[c];
     }
   }
   if (tr >= rows) return;
-  const float invP = 1.f / (float)P;
+  const double invP = 1.0 / (double)P;
   for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
-    float sc[8], sh[8], mean[8], invstd[8], k0[8], k1[8], k2[8];
+    float sc[8], sh[8], kA[8], kB[8], kC[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (has_bn) {
-        sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; invstd[i] = mi[C + c0 + i];
-        const float gi = gamma[c0 + i] * invstd[i];
-        k0[i] = gi;
-        k1[i] = training ? gi * (float)(acc[c0 + i]) * invP : 0.f;       // gamma*invstd*mean(dz)
-        k2[i] = training ? gi * (float)(acc[C + c0 + i]) * invP : 0.f;   // gamma*invstd*mean(dz*xhat)
+        sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i];
+        const float mean = mi[c0 + i], invstd = mi[C + c0 + i];
+        const float A = gamma[c0 + i] * invstd;
+        kA[i] = A;
+        if (training) {
+          const float cc = A * invstd * invstd * (float)(acc[C + c0 + i] * invP);
+          kC[i] = cc;
+          kB[i] = A * (float)(acc[c0 + i] * invP) - mean * cc;      // folded: -(y - mean)*cc = -y*cc + mean*cc
+        } else {
+          kC[i] = 0.f; kB[i] = 0.f;
+        }
       } else {
-        sc[i] = 1.f; sh[i] = 0.f; mean[i] = 0.f; invstd[i] = 1.f; k0[i] = 1.f; k1[i] = 0.f; k2[i] = 0.f;
+        sc[i] = 1.f; sh[i] = 0.f; kA[i] = 1.f; kB[i] = 0.f; kC[i] = 0.f;
       }
     }
-    for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += (long long)gridDim.x * rows) {
-      float dz[8], xh[8];
-      load_dz<T>(y, H, W, ldy, sc, sh, mean, invstd, has_bn, HC, WC, g1, ldg1, act1, g2, ldg2, act2, p, c0, dz, xh);
-      Vec8<T> o;
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
+      BwdIn<T> in[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = k0[i] * dz[i] - k1[i] - xh[i] * k2[i];
-      o.store(dy + p * lddy + c0);
+      for (int u = 0; u < 2; ++u)
+        if (p + u * stride < P) in[u].load(y, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (p + u * stride < P) {
+          float dz[8];
+          in[u].dz(sc, sh, act1, act2, two, dz);
+          Vec8<T> o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - in[u].y.v[i] * kC[i];
+          o.store(dy + (p + u * stride) * lddy + c0);
+        }
     }
   }
 }

@@ -367,19 +367,32 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
 __global__ void __launch_bounds__(256)
 adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restrict__ blocks,
             const float* __restrict__ hyper) {
+  __shared__ __nv_bfloat16 tile[16][16][18];   // [tap][d1 local][d0 local (+2 pad)] for the transposed packed copy
   const float step_size = hyper[6], inv_bc2_sqrt = hyper[7], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3],
               grad_scale = hyper[4];
   const int ti = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
   const stcgan_adam_tensor t = table[ti];
   const long long base = (long long)chunk * ADAM_CHUNK;
   if (t.d0 > 0) {
-    // packed gradients G[tap][d0][d1]: one thread owns one (d0,d1) pair = 16 contiguous parameters (64 B);
-    // its 16 gradient reads are coalesced across the warp (consecutive pairs of one tap plane).
+    // packed gradients G[tap][d0][d1]: one thread owns one (d0,d1) pair = 16 contiguous parameters (64 B).
+    // If the tensor also wants its bf16 tap-major copies refreshed (p1/p2 != NULL, d0 and d1 multiples of 16), a block
+    // covers a 16 x 16 tile of pairs so that P1[t][d0][d1] and the transposed P2[t][d1][d0] are written in 32-byte runs.
     const long long plane = (long long)t.d0 * t.d1;
-    const long long r = base / 16 + threadIdx.x;
-    if (r >= plane) return;
+    const bool tiled = t.p1 != nullptr;
+    int i0 = 0, i1 = 0, td0 = 0, td1 = 0;
+    long long r;
+    if (tiled) {
+      const int tiles1 = t.d1 / 16;
+      td0 = (chunk / tiles1) * 16; td1 = (chunk % tiles1) * 16;
+      i0 = threadIdx.x / 16; i1 = threadIdx.x % 16;
+      r = (long long)(td0 + i0) * t.d1 + td1 + i1;
+    } else {
+      r = base / 16 + threadIdx.x;
+      if (r >= plane) return;
+    }
     float* pp = t.p + r * 16; float* pm = t.m + r * 16; float* pv = t.v + r * 16;
     const bool vec = ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv)) & 15) == 0;
+    float pnew[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float p[4], m[4], v[4];
@@ -396,6 +409,7 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
       for (int k = 0; k < 4; ++k) {
         const float g = t.g[(long long)(4 * q + k) * plane + r] * grad_scale;
         adam_update(p[k], m[k], v[k], g, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+        pnew[4 * q + k] = p[k];
       }
       if (vec) {
         *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(p[0], p[1], p[2], p[3]);
@@ -405,6 +419,22 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k) { pp[4 * q + k] = p[k]; pm[4 * q + k] = m[k]; pv[4 * q + k] = v[k]; }
       }
+    }
+    if (tiled) {
+      __nv_bfloat16* p1 = static_cast<__nv_bfloat16*>(t.p1);
+      __nv_bfloat16* p2 = static_cast<__nv_bfloat16*>(t.p2);
+#pragma unroll
+      for (int tap = 0; tap < 16; ++tap) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(pnew[tap]);
+        p1[(long long)tap * plane + r] = h;                       // 16 consecutive d1 per tile row: 32-byte runs
+        tile[tap][i1][i0] = h;
+      }
+      __syncthreads();
+      // transposed copy: thread (j1 = tid / 16, j0 = tid % 16) writes P2[tap][td1 + j1][td0 + j0]
+      const int j1 = threadIdx.x / 16, j0 = threadIdx.x % 16;
+#pragma unroll
+      for (int tap = 0; tap < 16; ++tap)
+        p2[((long long)tap * t.d1 + td1 + j1) * t.d0 + td0 + j0] = tile[tap][j1][j0];
     }
   } else {
 #pragma unroll 4

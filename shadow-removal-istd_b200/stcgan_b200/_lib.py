@@ -34,7 +34,7 @@ class LossTerm(C.Structure):
 
 class AdamTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
-                ("n", C.c_int64), ("d0", C.c_int32), ("d1", C.c_int32)]
+                ("n", C.c_int64), ("d0", C.c_int32), ("d1", C.c_int32), ("p1", C.c_void_p), ("p2", C.c_void_p)]
 
 
 _i, _p, _f, _i64 = C.c_int, C.c_void_p, C.c_float, C.c_int64

@@ -58,6 +58,8 @@ class STCGANEngine:
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
         self.optim_D.set_packed_grads({**self.rt["D1"].param_grad_views, **self.rt["D2"].param_grad_views})
+        self.optim_G.set_pack_targets(self.rt["G1"].convs + self.rt["G2"].convs)
+        self.optim_D.set_pack_targets(self.rt["D1"].convs + self.rt["D2"].convs)
         self.pg = process_group
         self.world = 1
         if process_group is not None:

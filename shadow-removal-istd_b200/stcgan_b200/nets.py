@@ -78,6 +78,12 @@ class ConvOp:
             self.version = ver
         self.use_tc = act_dtype == torch.bfloat16
 
+    def mark_packed(self):
+        """The optimiser kernel refreshed p1/p2 from the updated weight: record the new version as packed."""
+        w = self.weight
+        if self.version is not None and self.thin is None:
+            self.version = (w._version, w.data_ptr(), self.version[2])
+
     def _backend_conv(self, k, nout, plain_epilogue=True):
         return BACKEND_TC if (self.use_tc and plain_epilogue and ops.tc_eligible_conv(k, nout)) else BACKEND_FFMA
 
@@ -145,6 +151,7 @@ class BNOp:
         self.m = bn_module
         self.c = bn_module.num_features
         self.ggamma = self.gbeta = None     # fp32 gradient views
+        self.shared_counter = False         # True: num_batches_tracked is a view into the runtime's flat counter tensor
 
     def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE):
         """stats (training) -> finalize -> apply.  scratch: dict with 'acc' (f64 [2,C]), 'mi', 'ss' (f32 [2,C])."""
@@ -158,15 +165,16 @@ class BNOp:
             ops.bn_finalize(scratch["acc"], n * h * w, m.weight.detach(), m.bias.detach(),
                             m.running_mean if use_running else None, m.running_var if use_running else None,
                             BN_MOMENTUM if m.momentum is None else m.momentum, m.eps, True, scratch["mi"], scratch["ss"])
-            if use_running and m.num_batches_tracked is not None:
+            if use_running and m.num_batches_tracked is not None and not self.shared_counter:
                 m.num_batches_tracked.add_(1)
         else:
             ops.bn_finalize(None, n * h * w, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var,
                             0.0, m.eps, False, scratch["mi"], scratch["ss"])
         ops.bn_act_apply(y, scratch["ss"], out1, act1, out2, act2)
 
-    def backward(self, y, scratch, training, g1, act1, g2, act2, dy, want_param_grads):
-        scratch["acc"].zero_()
+    def backward(self, y, scratch, training, g1, act1, g2, act2, dy, want_param_grads, zero_acc=True):
+        if zero_acc:
+            scratch["acc"].zero_()
         ops.bn_act_bwd(y, scratch["ss"], scratch["mi"], self.m.weight.detach(), training, g1, act1, g2, act2,
                        scratch["acc"], dy, self.ggamma if want_param_grads else None,
                        self.gbeta if want_param_grads else None)
@@ -178,6 +186,22 @@ def _bn_scratch(c, device):
             "ss": torch.empty((2, c), dtype=torch.float32, device=device)}
 
 
+class _BNArena:
+    """Per-pass BatchNorm scratch for a whole network: ONE zero-fill instead of one per layer."""
+
+    def __init__(self, channels, device):
+        tot = sum(channels)
+        self.acc = torch.zeros(2 * tot, dtype=torch.float64, device=device)
+        self.f32 = torch.empty(4 * tot, dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, c):
+        o = self.off
+        self.off += c
+        return {"acc": self.acc[2 * o:2 * o + 2 * c].view(2, c), "mi": self.f32[4 * o:4 * o + 2 * c].view(2, c),
+                "ss": self.f32[4 * o + 2 * c:4 * o + 4 * c].view(2, c)}
+
+
 class _NetRuntimeBase:
     """Holds ConvOps/BNOps of one network, the flat packed-gradient buffer and the Adam views."""
 
@@ -187,6 +211,15 @@ class _NetRuntimeBase:
         self.act_dtype = ops.DTYPES[precision][1]
         self.flat_grad = None
         self.param_grad_views = {}     # id(param) -> (view, d0, d1)  (d0 = 0 for non-packed gradients)
+        # num_batches_tracked of every BatchNorm becomes a view into one int64 tensor: one increment per forward pass
+        self.counters = None
+        tracked = [b for b in bns if b.m.track_running_stats and b.m.num_batches_tracked is not None]
+        if tracked and len(tracked) == len(bns):
+            dev = tracked[0].m.num_batches_tracked.device
+            self.counters = torch.stack([b.m.num_batches_tracked.detach().reshape(()) for b in tracked]).to(dev)
+            for i, b in enumerate(tracked):
+                b.m.num_batches_tracked = self.counters[i]
+                b.shared_counter = True
 
     def device(self):
         return self.convs[0].weight.device
@@ -278,7 +311,10 @@ class GeneratorRuntime(_NetRuntimeBase):
             inp_b = None
             inp = ops.pack_input(sources, self.cpad, dt)
         s = self.sizes(h, w)
-        ws = {"inp": inp, "inp_b": inp_b, "n": n, "s": s, "training": training, "y": [None] * (L + 1), "a": [None] * (L + 1),
+        arena = _BNArena([b.c for b in self.bns], dev)
+        if training and self.counters is not None:
+            self.counters.add_(1)
+        ws = {"inp": inp, "inp_b": inp_b, "n": n, "s": s, "training": training, "arena": arena, "y": [None] * (L + 1), "a": [None] * (L + 1),
               "cat": [None] * (L + 1), "uy": [None] * (L + 2), "bn_d": [None] * (L + 1), "bn_u": [None] * (L + 2)}
         C = [None] + [d.cout for d in self.downs]
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
@@ -293,7 +329,7 @@ class GeneratorRuntime(_NetRuntimeBase):
                 cat = new(hk, wk, 2 * C[k])
                 ws["a"][k], ws["cat"][k] = a, cat
                 if self.down_bns[k - 1] is not None:
-                    sc = _bn_scratch(C[k], dev)
+                    sc = arena.take(C[k])
                     ws["bn_d"][k] = sc
                     self.down_bns[k - 1].forward(y, sc, training, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU)
                 else:
@@ -310,7 +346,7 @@ class GeneratorRuntime(_NetRuntimeBase):
             up = self.ups[k - 1]
             uy = up.forward(x, 2 * hk, 2 * wk)
             ws["uy"][k] = uy
-            sc = _bn_scratch(up.cout, dev)
+            sc = arena.take(up.cout)
             ws["bn_u"][k] = sc
             dst = ws["cat"][k - 1]
             self.up_bns[k - 1].forward(uy, sc, training, dst[..., C[k - 1]:], ACT_RELU)   # crops to dst's H, W
@@ -329,6 +365,7 @@ class GeneratorRuntime(_NetRuntimeBase):
         n = ws["n"]
         C = [None] + [d.cout for d in self.downs]
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        ws["arena"].acc.zero_()            # all BatchNorm backward reductions of this pass accumulate into it
         # ---- outermost up conv (+Tanh)
         up = self.ups[0]
         if up.thin == "coutT":
@@ -346,7 +383,7 @@ class GeneratorRuntime(_NetRuntimeBase):
             up, bn, sc = self.ups[k - 1], self.up_bns[k - 1], ws["bn_u"][k]
             uy = ws["uy"][k]
             guy = torch.empty_like(uy)
-            bn.backward(uy, sc, training, dcat[..., C[k - 1]:], ACT_RELU, None, ACT_NONE, guy, param_grads)
+            bn.backward(uy, sc, training, dcat[..., C[k - 1]:], ACT_RELU, None, ACT_NONE, guy, param_grads, zero_acc=False)
             x_in = ws["cat"][k] if k < L else ws["a"][L]
             if param_grads:
                 up.wgrad(x_in, guy)
@@ -364,7 +401,7 @@ class GeneratorRuntime(_NetRuntimeBase):
                 skip_g = dcats[k][..., :C[k]]
                 bn = self.down_bns[k - 1]
                 if bn is not None:
-                    bn.backward(y, ws["bn_d"][k], training, da, ACT_LEAKY, skip_g, ACT_RELU, gy, param_grads)
+                    bn.backward(y, ws["bn_d"][k], training, da, ACT_LEAKY, skip_g, ACT_RELU, gy, param_grads, zero_acc=False)
                 else:
                     ops.bn_act_bwd(y, None, None, None, training, da, ACT_LEAKY, skip_g, ACT_RELU, None, gy, None, None)
             down = self.downs[k - 1]
@@ -407,7 +444,10 @@ class DiscriminatorRuntime(_NetRuntimeBase):
         else:
             inp_b, inp = None, ops.pack_input(sources, self.cpad, dt)
         nl = len(self.layers)
-        ws = {"inp": inp, "inp_b": inp_b, "n": n, "training": training, "y": [None] * nl, "a": [None] * nl,
+        arena = _BNArena([b.c for b in self.bns], dev)
+        if training and self.counters is not None:
+            self.counters.add_(1)
+        ws = {"inp": inp, "inp_b": inp_b, "n": n, "training": training, "arena": arena, "y": [None] * nl, "a": [None] * nl,
               "bn": [None] * nl, "s": [(h, w)]}
         x = None if thin_in else inp[..., :self.cin]
         for i, conv in enumerate(self.layers):
@@ -428,7 +468,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
             else:
                 y = conv.forward(x, oh, ow)
                 a = torch.empty_like(y)
-                sc = _bn_scratch(conv.cout, dev)
+                sc = arena.take(conv.cout)
                 ws["y"][i], ws["a"][i], ws["bn"][i] = y, a, sc
                 bn.forward(y, sc, training, a, ACT_LEAKY)
             x = a
@@ -439,6 +479,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
         nl = len(self.layers)
         n = ws["n"]
         last = self.layers[nl - 1]
+        ws["arena"].acc.zero_()
         oact = ACT_SIGMOID if self.use_sigmoid else ACT_NONE
         g_b = None
         if last.thin == "cout1":
@@ -457,7 +498,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                     ops.bn_act_bwd(ws["a"][i], None, None, None, training, g, ACT_LEAKY, None, ACT_NONE, None, gy, None, None)
                 else:
                     gy = torch.empty_like(ws["y"][i])
-                    bn.backward(ws["y"][i], ws["bn"][i], training, g, ACT_LEAKY, None, ACT_NONE, gy, param_grads)
+                    bn.backward(ws["y"][i], ws["bn"][i], training, g, ACT_LEAKY, None, ACT_NONE, gy, param_grads, zero_acc=False)
             else:
                 gy = g
             if i == nl - 1 and g_b is not None:

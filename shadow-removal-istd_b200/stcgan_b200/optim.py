@@ -25,11 +25,18 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._tables = {}        # group index -> dict(sig, table, blocks, nblocks, keep, hyper, hyper_host)
         self._packed_grads = {}  # id(param) -> (flat fp32 view, d0, d1): engine-provided packed gradients
+        self._pack_targets = {}  # id(param) -> ConvOp whose bf16 packed copies the Adam kernel refreshes in the same pass
         self.grad_scale = 1.0
 
     def set_packed_grads(self, views):
         """Engine hook: gradients that live in packed [16][d0][d1] layout instead of `p.grad`."""
         self._packed_grads = dict(views)
+        self._tables.clear()
+
+    def set_pack_targets(self, convs):
+        """Engine hook: ConvOps (with .weight, .p1, .p2, .mark_packed()) whose packed bf16 weights are rewritten by the
+        optimiser kernel itself, so no separate pack pass runs after the step."""
+        self._pack_targets = {id(c.weight): c for c in convs}
         self._tables.clear()
 
     def load_state_dict(self, state_dict):
@@ -65,7 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _build_table(self, group):
         chunk = _lib.load().stcgan_adam_chunk()
-        entries, blocks, keep = [], [], []
+        entries, blocks, keep, fused = [], [], [], []
         for p in group["params"]:
             gd = self._grad_of(p)
             if gd is None:
@@ -78,8 +85,14 @@ class FusedAdam(torch.optim.Optimizer):
                 if st[k].device != p.device or not st[k].is_contiguous():
                     st[k] = st[k].to(p.device).contiguous()
             ti = len(entries)
+            conv = self._pack_targets.get(id(p))
+            p1 = p2 = None
+            if (conv is not None and d0 > 0 and d0 % 16 == 0 and d1 % 16 == 0 and conv.p1 is not None
+                    and conv.p1.dtype == torch.bfloat16):
+                p1, p2 = conv.p1.data_ptr(), conv.p2.data_ptr()
+                fused.append(conv)
             entries.append(_lib.AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
-                                           st["exp_avg_sq"].data_ptr(), p.numel(), d0, d1))
+                                           st["exp_avg_sq"].data_ptr(), p.numel(), d0, d1, p1, p2))
             keep.append((p, g, st))
             blocks += [(ti, c) for c in range((p.numel() + chunk - 1) // chunk)]
         if not entries:
@@ -93,7 +106,7 @@ class FusedAdam(torch.optim.Optimizer):
         hyper_host = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(self.grad_scale), steps_done, 0.0, 0.0]
         hyper = torch.tensor(hyper_host, dtype=torch.float32, device=dev)
         return dict(sig=self._signature(group), table=table, blocks=blk, nblocks=len(blocks), keep=keep,
-                    hyper=hyper, hyper_host=hyper_host)
+                    hyper=hyper, hyper_host=hyper_host, fused=fused)
 
     def _sync_hyper(self, group, t):
         """Push lr / grad_scale changes (ExponentialLR steps once per epoch, src/cgan.py:383-384) to the device."""
@@ -135,4 +148,6 @@ class FusedAdam(torch.optim.Optimizer):
             for p, _, st in t["keep"]:
                 st["step"] += 1
                 torch.autograd.graph.increment_version(p)
+            for conv in t["fused"]:
+                conv.mark_packed()          # the kernel above already rewrote conv.p1 / conv.p2
         return loss

@@ -63,6 +63,13 @@ def test_engine_train_step_vs_oracle(cuda, lib, states, mode):
                 assert int(v) == int(ref.sd[n][k]) == (4 if n[0] == "D" else 1)
             if "running" in k:
                 assert rel_err(v, ref.sd[n][k]) < max(tol, 2e-2), (n, k)
+    # the optimiser kernel also refreshed the packed bf16 weight copies (no separate pack pass): check them
+    if mode == "bf16":
+        for n in nets:
+            for conv in eng.rt[n].convs:
+                w = conv.weight.detach()
+                assert torch.equal(conv.p1, w.permute(2, 3, 0, 1).reshape(16, conv.d0, conv.d1).to(torch.bfloat16)), n
+                assert torch.equal(conv.p2, w.permute(2, 3, 1, 0).reshape(16, conv.d1, conv.d0).to(torch.bfloat16)), n
     # post-Adam parameters: |delta| <= lr per element in the first step; compare the update direction statistically
     for n, lr in (("G1", 5e-4), ("G2", 5e-4), ("D1", 1e-4), ("D2", 1e-4)):
         agree, total = 0, 0
