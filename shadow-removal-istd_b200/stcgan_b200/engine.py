@@ -27,6 +27,33 @@ from .optim import FusedAdam
 SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss")
 
 
+class GradientSync:
+    """Data-parallel gradient exchange: SUM all-reduce of named flat gradient buffers over a process group (NCCL on the
+    GPUs, gloo in the CPU tests); the 1/world scale is applied inside the optimiser kernel.  `reduce(names, blocking,
+    pending)` launches the collectives asynchronously; a blocking call also waits for everything pending, which is how
+    the G2 bucket overlaps G1's backward while D's bucket gates `optim_D.step` (src/cgan.py:305)."""
+
+    def __init__(self, buffers, process_group=None):
+        self.buffers = buffers          # callable name -> tensor (buffers may be allocated lazily)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.log = []                   # (names, blocking) in call order, for tests
+
+    def reduce(self, names, blocking, pending):
+        self.log.append((tuple(names), bool(blocking)))
+        if self.world > 1:
+            import torch.distributed as dist
+            for n in names:
+                pending.append(dist.all_reduce(self.buffers(n), op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if blocking:
+            for wk in pending:
+                wk.wait()
+            pending.clear()
+
+
 @dataclass
 class TrainConfig:
     """Defaults of src/main.py:182-239; `ls` is what `args.D_loss_fn == "leastsqure"` evaluates to (always False)."""
@@ -60,11 +87,8 @@ class STCGANEngine:
         self.optim_D.set_packed_grads({**self.rt["D1"].param_grad_views, **self.rt["D2"].param_grad_views})
         self.optim_G.set_pack_targets(self.rt["G1"].convs + self.rt["G2"].convs)
         self.optim_D.set_pack_targets(self.rt["D1"].convs + self.rt["D2"].convs)
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None:
-            import torch.distributed as dist
-            self.world = dist.get_world_size(process_group)
+        self.sync = GradientSync(lambda n: self.rt[n].flat_grad, process_group)
+        self.pg, self.world = process_group, self.sync.world
         self.optim_G.grad_scale = self.optim_D.grad_scale = 1.0 / self.world
         self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
@@ -131,14 +155,7 @@ class STCGANEngine:
             r.ensure_packed()                                 # re-pack the updated weights for the next step
 
     def _reduce(self, names, blocking, pending):
-        if self.world > 1:
-            import torch.distributed as dist
-            for n in names:
-                pending.append(dist.all_reduce(self.rt[n].flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        if blocking:
-            for wk in pending:
-                wk.wait()
-            pending.clear()
+        self.sync.reduce(names, blocking, pending)
 
     # ------------------------------------------------------------------------------------------
     def train_step(self, x, m, y):
