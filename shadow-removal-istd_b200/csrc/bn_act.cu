@@ -355,9 +355,22 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static inline unsigned stream_grid(long long P, int rows) {
+// Grid for a grid-stride streaming kernel: exactly one wave of resident CTAs (148 SMs x occupancy), fewer for small
+// inputs.  `max_per_sm` caps it further for kernels that end in per-block atomics (fewer, fatter blocks).
+template <typename K>
+static inline unsigned stream_grid(long long P, int rows, K kernel, size_t smem, int max_per_sm = 8) {
+  // occupancy is queried once per kernel (before any CUDA-graph capture, during the warm-up steps) and cached
+  static const void* keys[32]; static int vals[32]; static int nkeys = 0;
+  int occ = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < nkeys; ++i) if (keys[i] == key) occ = vals[i];
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (nkeys < 32) { keys[nkeys] = key; vals[nkeys] = occ; ++nkeys; }
+  }
+  if (occ > max_per_sm) occ = max_per_sm;
   long long b = (P + rows - 1) / rows;
-  const long long cap = 148LL * 8;   // 8 resident 256-thread CTAs per SM, one wave
+  const long long cap = 148LL * occ;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (unsigned)b;
@@ -369,7 +382,7 @@ template <typename T>
 static int bn_stats_t(const void* y, long long P, int C, int ld, double* acc, int want_sq, cudaStream_t st) {
   const RowMap m = row_map(C);
   const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
-  bn_stats_kernel<T><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(static_cast<const T*>(y), P, C, ld, acc, m.cv, m.rows, want_sq);
+  bn_stats_kernel<T><<<stream_grid(P, m.rows * 8, bn_stats_kernel<T>, smem, 2), 256, smem, st>>>(static_cast<const T*>(y), P, C, ld, acc, m.cv, m.rows, want_sq);
   return finish_launch();
 }
 
@@ -401,11 +414,11 @@ int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, 
   if (PC == 0) return 0;
   const RowMap m = row_map(C);
   if (dtype == STCGAN_F32)
-    bn_act_apply_kernel<float><<<stream_grid(PC, m.rows * 2), 256, 0, st>>>(
+    bn_act_apply_kernel<float><<<stream_grid(PC, m.rows * 4, bn_act_apply_kernel<float>, 0), 256, 0, st>>>(
         static_cast<const float*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
         static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
   else
-    bn_act_apply_kernel<__nv_bfloat16><<<stream_grid(PC, m.rows * 2), 256, 0, st>>>(
+    bn_act_apply_kernel<__nv_bfloat16><<<stream_grid(PC, m.rows * 4, bn_act_apply_kernel<__nv_bfloat16>, 0), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
         static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
   return finish_launch();
@@ -421,11 +434,11 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
   const RowMap m = row_map(C);
   const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
   if (dtype == STCGAN_F32)
-    bn_bwd_reduce_kernel<float><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(
+    bn_bwd_reduce_kernel<float><<<stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 2), 256, smem, st>>>(
         static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
         static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 4), 256, smem, st>>>(
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 2), 256, smem, st>>>(
         static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
         act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
   return finish_launch();
@@ -443,11 +456,11 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
   if (P == 0) return 0;
   const RowMap m = row_map(C);
   if (dtype == STCGAN_F32)
-    bn_bwd_apply_kernel<float><<<stream_grid(P, m.rows * 2), 256, 0, st>>>(
+    bn_bwd_apply_kernel<float><<<stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<float>, 0), 256, 0, st>>>(
         static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
         act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 2), 256, 0, st>>>(
+    bn_bwd_apply_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<__nv_bfloat16>, 0), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
         static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
         static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
