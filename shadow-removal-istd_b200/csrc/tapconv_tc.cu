@@ -13,6 +13,8 @@
 // MMA issuer (one thread issues tcgen05.mma / tcgen05.commit).  Warps 2-5: epilogue (tcgen05.ld 32x32b, bias +
 // activation, 128-bit stores).  smem ring of STAGES x (A tile + B tile) guarded by full/empty mbarriers.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace stcgan {
@@ -187,7 +189,15 @@ struct alignas(64) TapGemmParams {
   int ksplit;
   float* part_out;
   int part_ld;
+  long long* dbg;          // optional per-CTA timestamps (8 x int64 per CTA), profiling aid (STCGAN_TC_DEBUG_TIMES)
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_T(slot) do { if (P.dbg) P.dbg[(((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
 
 template <int BN, int STAGES>
 struct TapGemmSmem {
@@ -222,6 +232,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   const int iters = taps_here * P.kchunks;
 
   if (threadIdx.x == 0) {
+    DBG_T(0);
     tma_prefetch_desc(&P.bmap);
     tma_prefetch_desc(&P.amap[0]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -233,6 +244,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_T(1);
 
   if (threadIdx.x == 0) {
     // ===== TMA producer =====
@@ -260,6 +272,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
+      if (it == 0) DBG_T(2);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
       const uint32_t b_addr = a_addr + SM::A_BYTES;
@@ -281,6 +294,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
     }
     umma_commit(tmem_full);
+    DBG_T(3);
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> bias/activation -> bf16 NHWC =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -291,6 +305,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     const bool valid = n < P.N && oy < P.OH && ox < P.OW;
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) DBG_T(4);
     tc_fence_after();
     if constexpr (BN == 16) {
       uint32_t r[16];
@@ -376,12 +391,14 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     }
   }
 
+  if (threadIdx.x == 64) DBG_T(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc<SM::TMEM_COLS>(tmem_base);
   }
+  if (threadIdx.x == 0) DBG_T(6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -611,8 +628,44 @@ static void choose_tile(int total, int GW, int GH, int N, int* wt, int* ht, int*
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// profiling aid: with STCGAN_TC_DEBUG_TIMES=<path> every tapgemm launch dumps per-CTA phase timestamps (synchronous!)
+static int dump_debug_times(const TapGemmParams& P0, dim3 grid, cudaStream_t st, int bn,
+                            int (*launch)(const TapGemmParams&, dim3, cudaStream_t)) {
+  const char* path = getenv("STCGAN_TC_DEBUG_TIMES");
+  if (!path) return launch(P0, grid, st);
+  TapGemmParams P = P0;
+  const size_t n = (size_t)grid.x * grid.y * grid.z * 8;
+  long long* d = nullptr;
+  cudaMalloc(&d, n * sizeof(long long));
+  cudaMemset(d, 0, n * sizeof(long long));
+  P.dbg = d;
+  int rc = launch(P, grid, st);
+  cudaStreamSynchronize(st);
+  long long* h = (long long*)malloc(n * sizeof(long long));
+  cudaMemcpy(h, d, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(path, "a");
+  if (f) {
+    fprintf(f, "launch bn=%d grid=%u,%u,%u iters=%d thin_k=%d ksplit=%d\n", bn, grid.x, grid.y, grid.z, P.ntaps * P.kchunks, P.thin_k, P.ksplit);
+    for (size_t c = 0; c < n / 8; ++c) {
+      for (int k = 0; k < 7; ++k) fprintf(f, "%lld ", h[c * 8 + k]);
+      fprintf(f, "\n");
+    }
+    fclose(f);
+  }
+  free(h); cudaFree(d);
+  return rc;
+}
+
+template <int BN, int STAGES>
+static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st);
+
 template <int BN, int STAGES>
 static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
+  return dump_debug_times(P, grid, st, BN, &launch_tapgemm_raw<BN, STAGES>);
+}
+
+template <int BN, int STAGES>
+static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
   using SM = TapGemmSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
