@@ -167,6 +167,7 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
                     T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   if (tr >= rows) return;
+  const float slope1 = act_slope(act1), slope2 = act_slope(act2);
   for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
     float sc[8], sh[8];
 #pragma unroll
@@ -196,8 +197,8 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float z = fmaf(v[u].v[i], sc[i], sh[i]);
-            a.v[i] = act_fwd(act1, z);
-            b.v[i] = act_fwd(act2, z);
+            a.v[i] = act_piecewise(z, slope1);
+            b.v[i] = act_piecewise(z, slope2);
           }
           a.store(o1 + p * ld1 + c0);
           if (o2) b.store(o2 + p * ld2 + c0);
@@ -235,9 +236,11 @@ struct BwdIn {
   // dz = g1*act1'(z) + g2*act2'(z),  z = y*sc + sh
   __device__ __forceinline__ void dz(const float* sc, const float* sh, int act1, int act2, bool two, float* out) const {
 #pragma unroll
+    const float s1 = act_slope(act1), s2 = act_slope(act2);
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float z = fmaf(y.v[i], sc[i], sh[i]);
-      out[i] = a.v[i] * act_gate(act1, z) + (two ? b.v[i] * act_gate(act2, z) : 0.f);
+      out[i] = a.v[i] * (z > 0.f ? 1.f : s1) + (two ? b.v[i] * (z > 0.f ? 1.f : s2) : 0.f);
     }
   }
 };

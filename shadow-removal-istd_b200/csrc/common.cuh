@@ -40,14 +40,18 @@ __device__ __forceinline__ float act_fwd(int act, float z) {
     default:                 return z;
   }
 }
+// Branch-free NONE / LeakyReLU(0.2) / ReLU for hot loops.  (act_fwd's switch also contains tanhf / expf; when the activation
+// code is a run-time value nvcc if-converts the switch and evaluates EVERY branch per element -- measured: 90 cycles per
+// element in the GEMM epilogue -- so streaming kernels must not call it.)
+__device__ __forceinline__ float act_slope(int act) {
+  return act == STCGAN_ACT_LEAKY ? 0.2f : (act == STCGAN_ACT_RELU ? 0.f : 1.f);
+}
+__device__ __forceinline__ float act_piecewise(float z, float slope) { return fmaxf(z, 0.f) + slope * fminf(z, 0.f); }
+
 // derivative of LeakyReLU(0.2)/ReLU w.r.t. its input, evaluated from the pre-activation z
 // (torch: leaky_relu_backward uses x > 0, threshold_backward uses x <= 0 -> 0)
 __device__ __forceinline__ float act_gate(int act, float z) {
-  switch (act) {
-    case STCGAN_ACT_LEAKY: return z > 0.f ? 1.f : 0.2f;
-    case STCGAN_ACT_RELU:  return z > 0.f ? 1.f : 0.f;
-    default:               return 1.f;
-  }
+  return z > 0.f ? 1.f : act_slope(act);
 }
 
 // ---------------------------------------------------------------------------------------------

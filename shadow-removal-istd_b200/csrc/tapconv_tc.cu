@@ -333,6 +333,8 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced
       constexpr int PITCH = BN * 2 + 16;
       const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
+      const float slope = act_slope(P.act);
+      const float* bias = P.bias;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -343,8 +345,8 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-            if (P.bias) { f0 += P.bias[n_col0 + c0 + v * 8 + 2 * e]; f1 += P.bias[n_col0 + c0 + v * 8 + 2 * e + 1]; }
-            f0 = act_fwd(P.act, f0); f1 = act_fwd(P.act, f1);
+            if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+            f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
             const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
             w[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
@@ -352,6 +354,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         }
       }
       __syncwarp();
+      if (threadIdx.x == 64) DBG_T(7);
       constexpr int LPR = BN * 2 / 16;     // lanes per output row (16-byte pieces)
       constexpr int RPI = 32 / LPR;        // rows per warp-wide store instruction
       const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
@@ -647,7 +650,7 @@ static int dump_debug_times(const TapGemmParams& P0, dim3 grid, cudaStream_t st,
   if (f) {
     fprintf(f, "launch bn=%d grid=%u,%u,%u iters=%d thin_k=%d ksplit=%d\n", bn, grid.x, grid.y, grid.z, P.ntaps * P.kchunks, P.thin_k, P.ksplit);
     for (size_t c = 0; c < n / 8; ++c) {
-      for (int k = 0; k < 7; ++k) fprintf(f, "%lld ", h[c * 8 + k]);
+      for (int k = 0; k < 8; ++k) fprintf(f, "%lld ", h[c * 8 + k]);
       fprintf(f, "\n");
     }
     fclose(f);
@@ -690,7 +693,9 @@ splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, cons
     const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
     float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) f[e] = act_fwd(act, f[e] + (bias ? bias[c + e] : 0.f));
+    const float slope = act_slope(act);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
     const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
