@@ -770,7 +770,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   P.Nout = n_rows;          // row pitch (per tap) of the packed weights
   if (thin_n) {
     dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), 1, (unsigned)g.nclass);
-    return launch_tapgemm<16, 5>(P, grid, st);
+    return launch_tapgemm<16, 3>(P, grid, st);    // 54 KB: four CTAs per SM (short K loops: latency-bound)
   }
   const int BN = Nout % 128 == 0 ? 128 : 64;
   // deep-K layers with few output tiles (the U-Net bottleneck): split the taps over extra CTAs, reduce in fp32
@@ -899,7 +899,7 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
       }
     }
   dim3 grid((unsigned)((D0 / 128) * (D1 / BN)), 16, (unsigned)splits);
-  if (BN == 128) return launch_wgrad<128, 4>(P, grid, st);
+  if (BN == 128) return launch_wgrad<128, 3>(P, grid, st);   // 96 KB: two CTAs per SM (6 stages per SM in flight)
   return launch_wgrad<64, 4>(P, grid, st);
 }
 
@@ -929,7 +929,7 @@ int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const 
   rc = encode_thin5d(&P.lmap[0], t, HP, WP, N, s, FW, FH, P.wt, P.ht, P.nt);
   if (rc) return rc;
   dim3 grid((unsigned)out_tiles, 1, (unsigned)splits);
-  if (BN == 128) return launch_wgrad<128, 4>(P, grid, st);
+  if (BN == 128) return launch_wgrad<128, 3>(P, grid, st);   // 96 KB: two CTAs per SM (6 stages per SM in flight)
   return launch_wgrad<64, 4>(P, grid, st);
 }
 
