@@ -225,6 +225,8 @@ def run_b200(args, rank, world, local_rank):
         t = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dt_e2e = t.tolist()
+    # the instrumented eager step contains the gradient all-reduces: every rank must run it
+    fam, eager_s = instrumented_breakdown(eng, x, m, y)
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -232,7 +234,6 @@ def run_b200(args, rank, world, local_rank):
     value, e2e_value = images / dt, images / dt_e2e
     flops_step = O.train_step_flops(H, W) * BATCH_PER_GPU
     # ---- roofline of the dominant kernel family, timed live with CUDA events ---------------------------------------
-    fam, eager_s = instrumented_breakdown(eng, x, m, y)
     tc_t = sum(v[0] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
     tc_f = sum(v[1] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
     tc_n = sum(v[2] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
