@@ -44,6 +44,29 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+// raw 8-channel loads, kept apart from the conversion so that several can be in flight per thread
+template <typename T> struct Raw8 { };
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+  __device__ __forceinline__ void unpack(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void unpack(float* v) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+
 // thread layout shared by all passes: CV = C/8 channel-vectors along x, pixels along y
 struct RowMap {
   int cv, rows;   // threads per pixel row, pixel rows per block
@@ -74,15 +97,19 @@ bn_stats_kernel(const T* __restrict__ y, long long P, int C, int ld, double* __r
     if (active) {
       const long long stride = (long long)gridDim.x * rows;
       for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
-        Vec8<T> v[4];
+        Raw8<T> raw[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)            // issue all loads before using any: 64 B in flight per thread
-          if (p + u * stride < P) v[u].load(y + (p + u * stride) * ld + c0);
+        for (int u = 0; u < 4; ++u) {          // unconditional (clamped) loads, all issued before any is consumed
+          const long long pp = p + u * stride;
+          raw[u].ld(y + (pp < P ? pp : P - 1) * ld + c0);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (p + u * stride < P) {
+            float v[8];
+            raw[u].unpack(v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += v[u].v[i]; q[i] = fmaf(v[u].v[i], v[u].v[i], q[i]); }
+            for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
           }
       }
     }
@@ -175,28 +202,29 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
     const long long stride = (long long)gridDim.x * rows;
     const bool nocrop = HC == H && WC == W;
     for (long long p0 = (long long)blockIdx.x * rows + tr; p0 < PC; p0 += 4 * stride) {
-      Vec8<T> v[4];
+      Raw8<T> raw[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const long long p = p0 + u * stride;
-        if (p < PC) {
-          long long src = p;
-          if (!nocrop) {
-            const int w = (int)(p % WC); const long long t = p / WC;
-            const int h = (int)(t % HC); const long long n = t / HC;
-            src = (n * H + h) * W + w;
-          }
-          v[u].load(y + src * (long long)ldy + c0);
+        long long p = p0 + u * stride;
+        if (p >= PC) p = PC - 1;                    // clamped: the load is unconditional, the store is not
+        long long src = p;
+        if (!nocrop) {
+          const int w = (int)(p % WC); const long long t = p / WC;
+          const int h = (int)(t % HC); const long long n = t / HC;
+          src = (n * H + h) * W + w;
         }
+        raw[u].ld(y + src * (long long)ldy + c0);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const long long p = p0 + u * stride;
         if (p < PC) {
           Vec8<T> a, b;
+          float yv[8];
+          raw[u].unpack(yv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float z = fmaf(v[u].v[i], sc[i], sh[i]);
+            const float z = fmaf(yv[i], sc[i], sh[i]);
             a.v[i] = act_piecewise(z, slope1);
             b.v[i] = act_piecewise(z, slope2);
           }
@@ -211,36 +239,37 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// raw operands of one pixel (8 channels): y, and the incoming gradients (zero outside the crop)
+// raw operands of one pixel (8 channels): y, and the incoming gradients (zero outside the crop).  `load` only issues
+// the (unconditional, clamped) global loads; `dz` converts and combines, so loads of several pixels overlap.
 template <typename T>
 struct BwdIn {
-  Vec8<T> y, a, b;
-  __device__ __forceinline__ void load(const T* yp, int H, int W, int ldy, int HC, int WC, const T* g1, int ldg1,
+  Raw8<T> ry, ra, rb;
+  bool inside;
+  __device__ __forceinline__ void load(const T* yp, long long P, int H, int W, int ldy, int HC, int WC, const T* g1, int ldg1,
                                        const T* g2, int ldg2, long long p, int c0) {
-    y.load(yp + p * ldy + c0);
+    if (p >= P) p = P - 1;
+    ry.ld(yp + p * ldy + c0);
     long long pc = p;
-    bool inside = true;
+    inside = true;
     if (HC != H || WC != W) {            // p indexes the FULL [N,H,W] grid; gradients live on the cropped grid
       const int w = (int)(p % W); const long long t = p / W;
       const int h = (int)(t % H); const long long n = t / H;
       inside = h < HC && w < WC;
-      pc = (n * HC + h) * WC + w;
+      pc = (n * HC + (h < HC ? h : HC - 1)) * WC + (w < WC ? w : WC - 1);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a.v[i] = 0.f; b.v[i] = 0.f; }
-    if (inside) {
-      a.load(g1 + pc * ldg1 + c0);
-      if (g2) b.load(g2 + pc * ldg2 + c0);
-    }
+    ra.ld(g1 + pc * ldg1 + c0);
+    if (g2) rb.ld(g2 + pc * ldg2 + c0); else rb.zero();
   }
-  // dz = g1*act1'(z) + g2*act2'(z),  z = y*sc + sh
-  __device__ __forceinline__ void dz(const float* sc, const float* sh, int act1, int act2, bool two, float* out) const {
-#pragma unroll
+  // dz = g1*act1'(z) + g2*act2'(z),  z = y*sc + sh ; also returns y
+  __device__ __forceinline__ void dz(const float* sc, const float* sh, int act1, int act2, bool two, float* out, float* yv) const {
+    float av[8], bv[8];
+    ry.unpack(yv); ra.unpack(av); rb.unpack(bv);
     const float s1 = act_slope(act1), s2 = act_slope(act2);
+    const float m = inside ? 1.f : 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(y.v[i], sc[i], sh[i]);
-      out[i] = a.v[i] * (z > 0.f ? 1.f : s1) + (two ? b.v[i] * (z > 0.f ? 1.f : s2) : 0.f);
+      const float z = fmaf(yv[i], sc[i], sh[i]);
+      out[i] = m * (av[i] * (z > 0.f ? 1.f : s1) + (two ? bv[i] * (z > 0.f ? 1.f : s2) : 0.f));
     }
   }
 };
@@ -265,15 +294,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
       for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
         BwdIn<T> in[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (p + u * stride < P) in[u].load(y, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+        for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
         for (int u = 0; u < 2; ++u)
           if (p + u * stride < P) {
-            float dz[8];
-            in[u].dz(sc, sh, act1, act2, two, dz);
+            float dz[8], yv[8];
+            in[u].dz(sc, sh, act1, act2, two, dz, yv);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], in[u].y.v[i] - mean[i], q[i]); }
+            for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], yv[i] - mean[i], q[i]); }
           }
       }
     }
@@ -339,16 +367,15 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
     for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
       BwdIn<T> in[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (p + u * stride < P) in[u].load(y, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+      for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
       for (int u = 0; u < 2; ++u)
         if (p + u * stride < P) {
-          float dz[8];
-          in[u].dz(sc, sh, act1, act2, two, dz);
+          float dz[8], yv[8];
+          in[u].dz(sc, sh, act1, act2, two, dz, yv);
           Vec8<T> o;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - in[u].y.v[i] * kC[i];
+          for (int i = 0; i < 8; ++i) o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - yv[i] * kC[i];
           o.store(dy + (p + u * stride) * lddy + c0);
         }
     }

@@ -871,10 +871,13 @@ static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_
   return finish_launch();
 }
 
-static bool use_persistent() {
+// STCGAN_TC_PERSISTENT: 0 = never, 1 = every full-width forward/dgrad launch, unset = thin-K layers only (measured on
+// B200: the operand stream of a 128-wide tile is bound by ~80 B/cycle/SM of TMA/L2 ingest, where 2 CTAs x 3 stages per SM
+// beat 1 persistent CTA x 5 stages; the 2048-tile / 2-iteration thin-K layers gain 20 % from persistence)
+static int persistent_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("STCGAN_TC_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  if (v < 0) { const char* e = getenv("STCGAN_TC_PERSISTENT"); v = !e ? 2 : (e[0] == '0' ? 0 : 1); }
+  return v;
 }
 
 // thin_n != 0: Nout <= 16 real output channels, wp packed with 16 (zero-padded) rows per tap; output goes to y32
@@ -988,7 +991,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
     return finish_launch();
   }
-  if (use_persistent()) {
+  if (persistent_mode() == 1) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, g.nclass, st);
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);
@@ -1036,7 +1039,7 @@ int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, 
   const int BN = Nout % 128 == 0 ? 128 : 64;
   rc = encode_2d(&P.bmap, wthin, 128, Nout, BN);
   if (rc) return rc;
-  if (use_persistent()) {
+  if (persistent_mode() != 0) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, 1, st);
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, 1, st);
