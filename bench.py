@@ -267,12 +267,66 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_infer(args, rank, world, local_rank):
+    """BASELINE configs[3]: G1 -> G2 inference at native ISTD resolution 640x480, batch 64, bf16, eval-mode BatchNorm
+    (src/cgan.py:437-446), uint8 quantisation on the GPU.  One replica per GPU (the path has no exchange step)."""
+    import stcgan_b200 as S
+    import stcgan_oracle as O
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, HH, WW = 64, 480, 640
+    torch.manual_seed(O.REFERENCE_SEED)
+    G1, G2 = S.UnetGenerator(3, 1).to(dev).eval(), S.UnetGenerator(4, 3).to(dev).eval()
+    xs = O.make_istd_batch(8, HH, WW, seed=42 + rank)[0].contiguous()
+    host = xs.repeat(B // 8, 1, 1, 1).contiguous().pin_memory()
+    x = host.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        S.infer(G1, G2, x)
+    torch.cuda.synchronize()
+    S._lib.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        S.infer(G1, G2, x)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = S._lib.launch_count()
+    dt = e0.elapsed_time(e1) * 1e-3
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x.copy_(host, non_blocking=True)
+        _, _, m8, y8 = S.infer(G1, G2, x)
+        m_host, y_host = m8.cpu(), y8.cpu()
+    e3.record()
+    torch.cuda.synchronize()
+    dt2 = e2.elapsed_time(e3) * 1e-3
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    flops = O.inference_flops(HH, WW) * B
+    line = {"metric": "stcgan_infer_images_per_sec_480x640_b64", "value": B * world * args.steps / dt, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "G1->G2 inference 480x640, batch 64, eval-mode BN, uint8 outputs (BASELINE configs[3])",
+                       "l2": "activations of one step (GBs) exceed the 126 MB L2", "parallelism": f"replicas x{world}",
+                       "algorithmic_gflop_per_image": O.inference_flops(HH, WW) / 1e9},
+            "e2e": {"value": B * world * args.steps / dt2, "unit": "images/s", "h2d_bytes_per_step": host.numel() * 4,
+                    "d2h_bytes_per_step": int(m_host.numel() + y_host.numel()), "ms_per_step": 1e3 * dt2 / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": flops / (dt / args.steps) / 1e12, "peak": peaks["tf_sustained"],
+                         "unit": "TFLOP/s", "frac": flops / (dt / args.steps) / 1e12 / peaks["tf_sustained"], "traffic": None,
+                         "kernel": "whole inference step (all kernels)", "peak_source": peaks["source"]}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -284,6 +338,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     if world != args.gpus and args.gpus > 1 and world == 1:
         raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    if args.workload == "infer":
+        run_infer(args, rank, world, local_rank)
+        return
     run_b200(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
