@@ -581,6 +581,199 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair forward / dgrad kernel (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN2 tile -- each CTA
+// owns 128 output pixels (its own A tile and its own 128 accumulator lanes in its own TMEM) and stages HALF of the
+// BN2-wide weight tile; the leader CTA's MMA thread issues tcgen05.mma.cta_group::2, which reads both halves.  Per SM
+// this halves the weight bytes that must be pulled through L2/TMA per FLOP (the measured limiter of the single-CTA
+// kernel: ~80 B/cycle/SM of operand ingest against the 128 B/cycle a 128x128 tile needs) and the smem read traffic.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier (executed by both CTAs of the pair)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint32_t leader_bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs once all prior MMAs of the pair have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+template <int BN2, int STAGES>
+struct PairSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;             // this CTA's 128 pixels
+  static constexpr int B_BYTES = (BN2 / 2) * TC_BK * 2;         // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PITCH = BN2 * 2 + 16;
+  static constexpr int RING = STAGES * STAGE_BYTES;
+  static constexpr int STAGING = TC_BM * PITCH;
+  static constexpr int BAR_OFFSET = RING > STAGING ? RING : STAGING;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN2, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
+tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
+  using SM = PairSmem<BN2, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cls = blockIdx.z;
+  const int n_col0 = blockIdx.y * BN2;
+  const int mt = blockIdx.x;                      // the pair (2i, 2i+1) shares blockIdx.y / z
+  const int tw = mt % P.tiles_w;
+  const int th = (mt / P.tiles_w) % P.tiles_h;
+  const int tn = mt / (P.tiles_w * P.tiles_h);    // may exceed the tensor for the padding CTA of an odd tile count: all OOB
+  const int b0 = tw * P.wt, a0 = th * P.ht, n0 = tn * P.nt;
+  const int iters = P.ntaps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&P.bmap);
+    tma_prefetch_desc(&P.amap[0]);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<BN2>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive / TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ===== TMA producer (both CTAs): own A tile + own half of B; bytes are credited to the leader's full barrier =====
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      const int j = it / P.kchunks, kc = it % P.kchunks;
+      uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+      uint8_t* b_dst = a_dst + SM::A_BYTES;
+      const uint32_t lbar = smem_u32(&full_bar[s]) & PEER_BIT_MASK;
+      if (leader) mbar_expect_tx(&full_bar[s], 2 * SM::STAGE_BYTES);
+      else mbar_arrive_cluster(lbar);
+      tma_load_4d_pair(&P.amap[P.tview[cls][j]], lbar, a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
+      tma_load_2d_pair(&P.bmap, lbar, b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0 + (int)rank * (BN2 / 2));
+    }
+  } else if (threadIdx.x == 32 && leader) {
+    // ===== MMA issuer (leader CTA only): 256 x BN2 x 16 per instruction across the pair =====
+    constexpr uint32_t idesc = make_idesc(256, BN2, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + SM::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < TC_BK / 16; ++k) {
+        const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+        const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+        umma_bf16_pair(tmem_base, ad, bd, idesc, (it | k) != 0);
+      }
+      umma_commit_pair(&empty_bar[s]);             // frees this stage in BOTH CTAs
+    }
+    umma_commit_pair(tmem_full);
+  } else if (warp >= 2) {
+    // ===== epilogue (both CTAs): own 128 rows x BN2 columns =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
+    const int a = a0 + hl, b = b0 + wl, n = n0 + nl;
+    const int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
+    const bool valid = n < P.N && oy < P.OH && ox < P.OW;
+    __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t stg = smem_u32(smem) + (uint32_t)row * SM::PITCH;
+    const float slope = act_slope(P.act);
+    const float* bias = P.bias;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN2; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+          if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+          f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
+      }
+    }
+    __syncwarp();
+    constexpr int LPR = BN2 * 2 / 16;    // 32 (BN2 = 256: one row per instruction) or 16
+    constexpr int RPI = 32 / LPR;
+    const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+    const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32) * SM::PITCH;
+#pragma unroll 4
+    for (int i = 0; i < 32; i += RPI) {
+      const int rr = i + lane / LPR;
+      const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+      if (pr) {
+        const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * SM::PITCH + (lane % LPR) * 16);
+        *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                              // the peer may still be reading this CTA's smem / arriving on its barriers
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_pair<BN2>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad kernel: G[tap][d0 tile 128][d1 tile BN] += sum over this CTA's pixel tiles
 // ---------------------------------------------------------------------------------------------
 struct alignas(64) WgradParams {
@@ -874,6 +1067,27 @@ static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_
 // STCGAN_TC_PERSISTENT: 0 = never, 1 = every full-width forward/dgrad launch, unset = thin-K layers only (measured on
 // B200: the operand stream of a 128-wide tile is bound by ~80 B/cycle/SM of TMA/L2 ingest, where 2 CTAs x 3 stages per SM
 // beat 1 persistent CTA x 5 stages; the 2048-tile / 2-iteration thin-K layers gain 20 % from persistence)
+template <int BN2, int STAGES>
+static int launch_tapgemm_pair(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st) {
+  using SM = PairSmem<BN2, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_pair_kernel<BN2, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, (unsigned)nclass);
+  tapgemm_tc_pair_kernel<BN2, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  return finish_launch();
+}
+
+// STCGAN_TC_PAIR: 1 = use the CTA-pair (cta_group::2) kernel for full-width forward/dgrad launches with Nout % 128 == 0
+static int pair_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STCGAN_TC_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
 static int persistent_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("STCGAN_TC_PERSISTENT"); v = !e ? 2 : (e[0] == '0' ? 0 : 1); }
@@ -990,6 +1204,10 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     long long blocks = (Ppix * (Nout / 4) + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
     splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
     return finish_launch();
+  }
+  if (pair_mode() == 1 && Nout % 256 == 0) {       // each CTA stages 128 of the 256 weight rows: same TMA box as BN = 128
+    const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
+    return launch_tapgemm_pair<256, 3>(P, m_tiles, Nout / 256, g.nclass, st);
   }
   if (persistent_mode() == 1) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
