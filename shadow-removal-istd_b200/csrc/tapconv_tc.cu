@@ -671,6 +671,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
   const int iters = P.ntaps * P.kchunks;
 
   if (threadIdx.x == 0) {
+    DBG_T(0);
     tma_prefetch_desc(&P.bmap);
     tma_prefetch_desc(&P.amap[0]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
@@ -682,6 +683,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
   cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG_T(1);
 
   if (threadIdx.x == 0) {
     // ===== TMA producer (both CTAs): own A tile + own half of B; bytes are credited to the leader's full barrier =====
@@ -705,6 +707,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
+      if (it == 0) DBG_T(2);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
       const uint32_t b_addr = a_addr + SM::A_BYTES;
@@ -717,6 +720,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
       umma_commit_pair(&empty_bar[s]);             // frees this stage in BOTH CTAs
     }
     umma_commit_pair(tmem_full);
+    DBG_T(3);
   } else if (warp >= 2) {
     // ===== epilogue (both CTAs): own 128 rows x BN2 columns =====
     const int q = warp & 3;
@@ -727,6 +731,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
     const bool valid = n < P.N && oy < P.OH && ox < P.OW;
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) DBG_T(4);
     tc_fence_after();
     const uint32_t stg = smem_u32(smem) + (uint32_t)row * SM::PITCH;
     const float slope = act_slope(P.act);
@@ -765,12 +770,14 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
     }
   }
 
+  if (threadIdx.x == 64) DBG_T(5);
   tc_fence_before();
   cluster_sync_all();                              // the peer may still be reading this CTA's smem / arriving on its barriers
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc_pair<BN2>(tmem_base);
   }
+  if (threadIdx.x == 0) DBG_T(6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1068,7 +1075,7 @@ static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_
 // B200: the operand stream of a 128-wide tile is bound by ~80 B/cycle/SM of TMA/L2 ingest, where 2 CTAs x 3 stages per SM
 // beat 1 persistent CTA x 5 stages; the 2048-tile / 2-iteration thin-K layers gain 20 % from persistence)
 template <int BN2, int STAGES>
-static int launch_tapgemm_pair(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st) {
+static int launch_tapgemm_pair_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
   using SM = PairSmem<BN2, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -1076,12 +1083,20 @@ static int launch_tapgemm_pair(const TapGemmParams& P, int m_tiles, int n_tiles,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, (unsigned)nclass);
   tapgemm_tc_pair_kernel<BN2, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
   return finish_launch();
 }
 
-// STCGAN_TC_PAIR: 1 = use the CTA-pair (cta_group::2) kernel for full-width forward/dgrad launches with Nout % 128 == 0
+template <int BN2, int STAGES>
+static int launch_tapgemm_pair(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st) {
+  dim3 grid((unsigned)((m_tiles + 1) / 2 * 2), (unsigned)n_tiles, (unsigned)nclass);
+  return dump_debug_times(P, grid, st, -BN2, &launch_tapgemm_pair_raw<BN2, STAGES>);
+}
+
+// STCGAN_TC_PAIR: 1 = use the CTA-pair (cta_group::2) kernel for full-width forward/dgrad launches with Nout % 256 == 0.
+// Opt-in: it is parity-green (all GPU tests pass with it) but measured SLOWER than the single-CTA kernel on B200 so far:
+// the leader's main loop runs at 0.9 us per 256x256x64 step against 0.42 us per 128x128x64 step of the single-CTA kernel
+// (profiles/r01_tapgemm_cta_phase_times.txt); the operand stream per CTA, not the tensor pipe, is the limiter in both.
 static int pair_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("STCGAN_TC_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
