@@ -258,9 +258,8 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
       if (P.thin_k) {
         // one 64-byte line per (pixel, kernel row): TMA gives every inner line its own swizzle-span row, so the two
-        // kernel rows of this K chunk are two separate [128 px][64 B] SWIZZLE_64B blocks
-        tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, 2 * kc, b0, a0, n0);
-        tma_load_5d(&P.amap[0], &full_bar[s], a_dst + 8192, 0, 2 * kc + 1, b0, a0, n0);
+        // kernel rows of this K chunk are two consecutive [128 px][64 B] SWIZZLE_64B blocks (kernel row = slowest box dim)
+        tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, b0, a0, n0, 2 * kc);   // both kernel rows in one instruction
       } else
         tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
       tma_load_2d(&P.bmap, &full_bar[s], b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0);
@@ -471,8 +470,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
         uint8_t* b_dst = a_dst + SM::A_BYTES;
         mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
         if (P.thin_k) {
-          tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, 2 * kc, b0, a0, n0);
-          tma_load_5d(&P.amap[0], &full_bar[s], a_dst + 8192, 0, 2 * kc + 1, b0, a0, n0);
+          tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, b0, a0, n0, 2 * kc);
         } else {
           tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
         }
@@ -854,19 +852,14 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
       uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
       uint8_t* b_dst = a_dst + SM::A_BYTES;
       mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+      // two TMA instructions per stage: every operand tile (2 or BN/64 channel blocks, or the 4 kernel rows of the thin
+      // im2col view) is one 5-D box whose slowest dimension enumerates the [64 px][row] blocks
       if (P.thin) {
-#pragma unroll
-        for (int kh = 0; kh < 4; ++kh)    // four [64 px][64 B] SWIZZLE_64B blocks: M rows (kh, kw, c)
-          tma_load_5d(&P.lmap[0], &full_bar[s], a_dst + kh * 4096, 0, kh, b0, a0, n0);
-#pragma unroll
-        for (int h = 0; h < BN / 64; ++h)
-          tma_load_4d(&P.smap, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0, a0, n0);
+        tma_load_5d(&P.lmap[0], &full_bar[s], a_dst, 0, b0, a0, n0, 0);                       // M rows (kh, kw, c)
+        tma_load_5d(&P.smap, &full_bar[s], b_dst, 0, b0, a0, n0, d1_0 / 64);                  // N = BN channels of F
       } else {
-        tma_load_4d(&P.smap, &full_bar[s], a_dst, d0_0, b0, a0, n0);
-        tma_load_4d(&P.smap, &full_bar[s], a_dst + 8192, d0_0 + 64, b0, a0, n0);
-#pragma unroll
-        for (int h = 0; h < BN / 64; ++h)
-          tma_load_4d(lm, &full_bar[s], b_dst + h * 8192, d1_0 + h * 64, b0 + P.tdx[tap], a0 + P.tdy[tap], n0);
+        tma_load_5d(&P.smap, &full_bar[s], a_dst, 0, b0, a0, n0, d0_0 / 64);                  // M = 128 channels of S
+        tma_load_5d(lm, &full_bar[s], b_dst, 0, b0 + P.tdx[tap], a0 + P.tdy[tap], n0, d1_0 / 64);   // N = BN channels of L
       }
     }
   } else if (threadIdx.x == 32) {
@@ -1235,18 +1228,37 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
 }
 
 // 5D im2col view of a zero-bordered 8-channel tensor T [N, HP, WP, 8]:
-//   (d0 = (kw, c): 32 contiguous elements, d1 = kernel row kh (4), d2 = grid column, d3 = grid row, d4 = image)
-//   element address = ((n*HP + s*gy + kh)*WP + s*gx)*8 + d0       box = (32, 1, wt, ht, nt) -> [pixel][64 B], SWIZZLE_64B
+//   (d0 = (kw, c): 32 contiguous elements = 64 B, d1 = grid column, d2 = grid row, d3 = image, d4 = kernel row kh)
+//   element address = ((n*HP + s*gy + kh)*WP + s*gx)*8 + d0
+//   box = (32, wt, ht, nt, box_kh) -> box_kh consecutive [pixel][64 B] SWIZZLE_64B blocks from ONE TMA instruction
 static int encode_thin5d(CUtensorMap* m, const void* base, long long HP, long long WP, long long N, int s,
-                         long long GW, long long GH, int bw, int bh, int bn) {
+                         long long GW, long long GH, int bw, int bh, int bn, int box_kh) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return (int)cudaErrorNotSupported;
-  cuuint64_t dims[5] = {32, 4, (cuuint64_t)GW, (cuuint64_t)GH, (cuuint64_t)N};
-  cuuint64_t strides[4] = {(cuuint64_t)WP * 16, (cuuint64_t)s * 16, (cuuint64_t)s * WP * 16, (cuuint64_t)HP * WP * 16};
-  cuuint32_t box[5] = {32, 1, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint64_t dims[5] = {32, (cuuint64_t)GW, (cuuint64_t)GH, (cuuint64_t)N, 4};
+  cuuint64_t strides[4] = {(cuuint64_t)s * 16, (cuuint64_t)s * WP * 16, (cuuint64_t)HP * WP * 16, (cuuint64_t)WP * 16};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)box_kh};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// NHWC bf16 tensor with the channel dimension split in blocks of 64: dims (64, W, H, N, C/64); box (64, bw, bh, bn, nblk)
+// -> nblk consecutive [pixel][128 B] SWIZZLE_128B blocks (an MN-major operand of 64*nblk channels) from ONE TMA instruction
+static int encode_nhwc_blk(CUtensorMap* m, const void* base, long long C, long long W, long long H, long long N,
+                           long long sw, long long sh, long long sn, int bw, int bh, int bn, int nblk) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return (int)cudaErrorNotSupported;
+  if (W < 1) W = 1;
+  if (H < 1) H = 1;
+  cuuint64_t dims[5] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)(C / 64)};
+  cuuint64_t strides[4] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2, 128};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)nblk};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
@@ -1266,7 +1278,7 @@ int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, 
   P.GH = OH; P.GW = OW; P.N = N; P.OH = OH; P.OW = OW; P.ostride = 1;
   P.ntaps = 1; P.kchunks = 2; P.thin_k = 1;
   P.Nout = Nout; P.nout_real = Nout; P.ldy = ldy; P.act = act; P.bias = bias; P.y = static_cast<__nv_bfloat16*>(y);
-  int rc = encode_thin5d(&P.amap[0], t, HP, WP, N, s, OW, OH, P.wt, P.ht, P.nt);
+  int rc = encode_thin5d(&P.amap[0], t, HP, WP, N, s, OW, OH, P.wt, P.ht, P.nt, 2);
   if (rc) return rc;
   for (int v = 1; v < 4; ++v) P.amap[v] = P.amap[0];
   const int BN = Nout % 128 == 0 ? 128 : 64;
@@ -1314,19 +1326,19 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
 
   const __nv_bfloat16* sb = static_cast<const __nv_bfloat16*>(S);
   const __nv_bfloat16* lb = static_cast<const __nv_bfloat16*>(L);
-  int rc = encode_nhwc(&P.smap, sb, D0, SW, SH, N, lds, (long long)SW * lds, (long long)SH * SW * lds, P.wt, P.ht, P.nt);
+  int rc = encode_nhwc_blk(&P.smap, sb, D0, SW, SH, N, lds, (long long)SW * lds, (long long)SH * SW * lds, P.wt, P.ht, P.nt, 2);
   if (rc) return rc;
   const long long sn = (long long)LH * LW * ldl;
   const int stride = geom == STCGAN_GEOM_WIN_S2 ? 2 : 1;
   if (stride == 1) {
-    rc = encode_nhwc(&P.lmap[0], lb, D1, LW, LH, N, ldl, (long long)LW * ldl, sn, P.wt, P.ht, P.nt);
+    rc = encode_nhwc_blk(&P.lmap[0], lb, D1, LW, LH, N, ldl, (long long)LW * ldl, sn, P.wt, P.ht, P.nt, BN / 64);
     if (rc) return rc;
     for (int v = 1; v < 4; ++v) P.lmap[v] = P.lmap[0];
   } else {
     for (int p = 0; p < 2; ++p)
       for (int q = 0; q < 2; ++q) {
-        rc = encode_nhwc(&P.lmap[p * 2 + q], lb + ((long long)p * LW + q) * ldl, D1, (LW - q + 1) / 2, (LH - p + 1) / 2, N,
-                         2LL * ldl, 2LL * LW * ldl, sn, P.wt, P.ht, P.nt);
+        rc = encode_nhwc_blk(&P.lmap[p * 2 + q], lb + ((long long)p * LW + q) * ldl, D1, (LW - q + 1) / 2, (LH - p + 1) / 2, N,
+                             2LL * ldl, 2LL * LW * ldl, sn, P.wt, P.ht, P.nt, BN / 64);
         if (rc) return rc;
       }
   }
@@ -1367,9 +1379,9 @@ int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const 
   if (splits < 1) splits = 1;
   P.tiles_per_split = (total_tiles + splits - 1) / splits;
   splits = (total_tiles + P.tiles_per_split - 1) / P.tiles_per_split;
-  int rc = encode_nhwc(&P.smap, f, Dfat, FW, FH, N, ldf, (long long)FW * ldf, (long long)FH * FW * ldf, P.wt, P.ht, P.nt);
+  int rc = encode_nhwc_blk(&P.smap, f, Dfat, FW, FH, N, ldf, (long long)FW * ldf, (long long)FH * FW * ldf, P.wt, P.ht, P.nt, BN / 64);
   if (rc) return rc;
-  rc = encode_thin5d(&P.lmap[0], t, HP, WP, N, s, FW, FH, P.wt, P.ht, P.nt);
+  rc = encode_thin5d(&P.lmap[0], t, HP, WP, N, s, FW, FH, P.wt, P.ht, P.nt, 4);
   if (rc) return rc;
   dim3 grid((unsigned)out_tiles, 1, (unsigned)splits);
   if (BN == 128) return launch_wgrad<128, 3>(P, grid, st);   // 96 KB: two CTAs per SM (6 stages per SM in flight)
