@@ -235,6 +235,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     DBG_T(0);
     tma_prefetch_desc(&P.bmap);
     tma_prefetch_desc(&P.amap[0]);
+    tma_prefetch_desc(&P.amap[1]);
+    tma_prefetch_desc(&P.amap[2]);
+    tma_prefetch_desc(&P.amap[3]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -444,6 +447,9 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&P.bmap);
     tma_prefetch_desc(&P.amap[0]);
+    tma_prefetch_desc(&P.amap[1]);
+    tma_prefetch_desc(&P.amap[2]);
+    tma_prefetch_desc(&P.amap[3]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
     fence_barrier_init();
@@ -672,6 +678,9 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
     DBG_T(0);
     tma_prefetch_desc(&P.bmap);
     tma_prefetch_desc(&P.amap[0]);
+    tma_prefetch_desc(&P.amap[1]);
+    tma_prefetch_desc(&P.amap[2]);
+    tma_prefetch_desc(&P.amap[3]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -1096,6 +1105,16 @@ static int pair_mode() {
   return v;
 }
 
+// accumulator width of the single-CTA kernel.  STCGAN_TC_BN256=1 selects 128x256 tiles (2 stages, 2 CTAs/SM) where the layer
+// allows it; measured on B200 it is parity-green but 12 % slower on the conv launches of a train step than 128x128 tiles
+// with 3 stages, so the default stays 128.
+static int bn_select(int Nout) {
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("STCGAN_TC_BN256"); wide = (e && e[0] == '1') ? 1 : 0; }
+  if (wide && Nout % 256 == 0) return 256;
+  return Nout % 128 == 0 ? 128 : 64;
+}
+
 static int persistent_mode() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("STCGAN_TC_PERSISTENT"); v = !e ? 2 : (e[0] == '0' ? 0 : 1); }
@@ -1170,7 +1189,20 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
         if (rc) return rc;
       }
   }
-  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (Nout % 128 == 0 ? 128 : 64));
+  // deep-K layers with few output tiles (the U-Net bottleneck) split their taps over extra CTAs and reduce in fp32; that
+  // path keeps 128-wide tiles (its fp32 staging tile must fit the pipeline smem)
+  int BNsel = bn_select(Nout);
+  int ksplit = 1;
+  if (!thin_n && Nout % 64 == 0) {
+    const int bn_s = Nout % 128 == 0 ? 128 : 64;
+    const long long ctas_s = (long long)P.tiles_w * P.tiles_h * tiles_n * (Nout / bn_s) * g.nclass;
+    const long long need_s = (long long)g.N * g.OH * g.OW * Nout * 4;
+    if (ws && ws_bytes >= need_s && ctas_s <= 74 && g.ntaps * P.kchunks >= 32) {
+      while (ksplit * 2 <= g.ntaps && ctas_s * ksplit * 2 <= 296) ksplit *= 2;
+      if (ksplit > 1) BNsel = bn_s;
+    }
+  }
+  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 ? 128 : BNsel));
   if (rc) return rc;
 
   for (int c = 0; c < g.nclass; ++c)
@@ -1194,35 +1226,32 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), 1, (unsigned)g.nclass);
     return launch_tapgemm<16, 3>(P, grid, st);    // 54 KB: four CTAs per SM (short K loops: latency-bound)
   }
-  const int BN = Nout % 128 == 0 ? 128 : 64;
+  const int BN = BNsel;
   // deep-K layers with few output tiles (the U-Net bottleneck): split the taps over extra CTAs, reduce in fp32
-  const long long ctas = (long long)P.tiles_w * P.tiles_h * tiles_n * (Nout / BN) * g.nclass;
   const long long need = (long long)g.N * g.OH * g.OW * Nout * 4;
-  int ksplit = 1;
-  if (ws && ws_bytes >= need && ctas <= 74 && g.ntaps * P.kchunks >= 32)
-    while (ksplit * 2 <= g.ntaps && ctas * ksplit * 2 <= 296) ksplit *= 2;
   if (ksplit > 1) {
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
     if (e != cudaSuccess) return (int)e;
     P.ksplit = ksplit; P.part_out = ws; P.part_ld = Nout;
     dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)(g.nclass * ksplit));
-    rc = BN == 128 ? launch_tapgemm<128, 3>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
+    rc = BN == 256 ? launch_tapgemm<256, 2>(P, grid, st) : BN == 128 ? launch_tapgemm<128, 3>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
     if (rc) return rc;
     const long long Ppix = (long long)g.N * g.OH * g.OW;
     long long blocks = (Ppix * (Nout / 4) + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
     splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
     return finish_launch();
   }
-  if (pair_mode() == 1 && Nout % 256 == 0) {       // each CTA stages 128 of the 256 weight rows: same TMA box as BN = 128
+  if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     return launch_tapgemm_pair<256, 3>(P, m_tiles, Nout / 256, g.nclass, st);
   }
-  if (persistent_mode() == 1) {
+  if (persistent_mode() == 1 && BN != 256) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, g.nclass, st);
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);
   }
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
+  if (BN == 256) return launch_tapgemm<256, 2>(P, grid, st);
   if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
   return launch_tapgemm<64, 4>(P, grid, st);
 }
