@@ -319,3 +319,35 @@ def test_thin_layers_on_tensor_cores(cuda, lib, case):
     gw = ops.unpack_grad(op.g, op.d0, op.d1)
     torch.cuda.synchronize()
     assert rel_err(gw, wd.grad) < 2e-5, "thin wgrad"
+
+
+@pytest.mark.parametrize("env", [{"STCGAN_TC_PERSISTENT": "1"}, {"STCGAN_TC_PAIR": "1"}, {"STCGAN_TC_BN256": "1"},
+                                 {"STCGAN_TC_PERSISTENT": "0"}], ids=lambda e: "-".join(f"{k[10:]}={v}" for k, v in e.items()))
+def test_optional_tensor_core_kernels_stay_parity_green(cuda, lib, env):
+    """The persistent (TMEM double-buffered), CTA-pair (tcgen05 cta_group::2) and 128x256-tile variants of the tap-GEMM are
+    selected by environment variables read once per process, so each runs in a child process: D2's forward + backward
+    (c2..c4 exercise every variant: Nout 128 / 256 / 512, stride 2 and 1) against the float64 oracle."""
+    import os, subprocess, sys, textwrap
+    from conftest import ROOT
+    code = textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {os.path.join(ROOT, 'shadow-removal-istd_b200')!r}); sys.path.insert(0, {os.path.join(ROOT, 'oracle')!r})
+        import torch, stcgan_b200 as S, stcgan_oracle as O
+        st = O.build_all_states()["D2"]
+        d = S.NLayerDiscriminator(7); d.load_state_dict(st); d.cuda().train()
+        x, m, y = O.make_istd_batch(4, 256, 256)
+        inp = torch.cat((x, m, y), 1)
+        xi = inp.cuda().requires_grad_(True)
+        out = d(xi); out.sum().backward(); torch.cuda.synchronize()
+        sd = {{k: (v.double() if v.is_floating_point() else v.clone()) for k, v in st.items()}}
+        for k in O.trainable_keys(sd): sd[k].requires_grad_(True)
+        xr = inp.double().requires_grad_(True)
+        ref = O.discriminator_forward(sd, xr, training=True); ref.sum().backward()
+        rel = lambda a, b: float((a.double().cpu() - b).norm() / b.norm())
+        e_out, e_dx = rel(out, ref), rel(xi.grad, xr.grad)
+        e_w = max(rel(p.grad, sd[k].grad) for k, p in d.named_parameters())
+        print("ERR", e_out, e_dx, e_w)
+        assert e_out < 2e-2 and e_dx < 0.5 and e_w < 0.5
+    """)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
