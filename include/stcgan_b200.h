@@ -238,6 +238,11 @@ int stcgan_adam_chunk(void);
  * replaces `*0.5+0.5` (src/cgan.py:441-442) + utils.float2uint (src/utils.py:65-67) + CHW->HWC transpose
  * (cgan.py:443-446): u8[n,h,w,c] = (uint8) trunc(clip(v*0.5+0.5, 0, 1) * 255), all in fp32 like numpy. */
 int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream);
+/* ---- input pre-processing on the GPU ----------------------------------------------------------------
+ * replaces utils.uint2float (src/utils.py:60-62: astype(float32)/255) + the ISTDDataset normalisation and HWC->CHW
+ * transpose (src/dataset.py:152: (s.transpose(2,0,1) - 0.5) * 2): uint8 [N,H,W,C] -> float32 [N,C,H,W], bit-exact with
+ * numpy's float32 arithmetic, so the host only ships the decoded uint8 images (4x fewer H2D bytes). */
+int stcgan_u8_hwc_to_nchw_f32(const uint8_t* in_nhwc, int N, int H, int W, int C, float* out_nchw, void* stream);
 /* plain float2uint on a flat array (known-answer tests) */
 int stcgan_float2uint(const float* in, int64_t n, uint8_t* out, void* stream);
 

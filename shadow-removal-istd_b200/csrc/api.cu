@@ -48,6 +48,7 @@ int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H
 int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st);
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st);
 int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st);
+int u8_to_nchw(const uint8_t* in, int N, int H, int W, int C, float* out, cudaStream_t st);
 int float2uint_hwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
 }  // namespace stcgan
 
@@ -234,6 +235,11 @@ int stcgan_adam_chunk(void) { return 256 * 16; }
 int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream) {
   STCGAN_REQUIRE(nchw && out_nhwc);
   return float2uint_hwc(nchw, N, C, H, W, out_nhwc, as_stream(stream));
+}
+
+int stcgan_u8_hwc_to_nchw_f32(const uint8_t* in_nhwc, int N, int H, int W, int C, float* out_nchw, void* stream) {
+  STCGAN_REQUIRE(in_nhwc && out_nchw && N >= 0 && H > 0 && W > 0 && C > 0);
+  return u8_to_nchw(in_nhwc, N, H, W, C, out_nchw, as_stream(stream));
 }
 
 int stcgan_float2uint(const float* in, int64_t n, uint8_t* out, void* stream) {

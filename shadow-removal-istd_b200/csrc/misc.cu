@@ -492,6 +492,28 @@ float2uint_hwc_kernel(const float* __restrict__ in, int N, int C, long long HW, 
   }
 }
 
+// dataset transform on the GPU: uint8 HWC image -> float32 CHW in [-1, 1], exactly as src/utils.py:60-62 (astype(float32)/255)
+// followed by src/dataset.py:152 ((s.transpose(2,0,1) - 0.5) * 2), every step rounded to float32 like numpy
+__global__ void __launch_bounds__(256)
+u8_to_nchw_kernel(const uint8_t* __restrict__ in, int N, int C, long long HW, float* __restrict__ out) {
+  const long long P = (long long)N * HW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, r = p % HW;
+    for (int c = 0; c < C; ++c) {
+      const float f = __fdiv_rn((float)in[p * C + c], 255.f);
+      out[(n * C + c) * HW + r] = __fmul_rn(__fsub_rn(f, 0.5f), 2.f);
+    }
+  }
+}
+
+int u8_to_nchw(const uint8_t* in, int N, int H, int W, int C, float* out, cudaStream_t st) {
+  const long long HW = (long long)H * W, P = N * HW;
+  if (P == 0 || C == 0) return 0;
+  long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  u8_to_nchw_kernel<<<(unsigned)b, 256, 0, st>>>(in, N, C, HW, out);
+  return finish_launch();
+}
+
 int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st) {
   if (n == 0) return 0;
   long long b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;

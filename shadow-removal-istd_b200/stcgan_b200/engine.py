@@ -216,6 +216,18 @@ class STCGANEngine:
         self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
         return self.losses
 
+    def replay_u8(self, x8, m8, y8):
+        """Captured step fed with decoded uint8 HWC images ([B,H,W,3], [B,H,W,1], [B,H,W,3]; host-pinned or device): the
+        dataset's uint8 -> [-1,1] float CHW transform (src/dataset.py:100-110,152) runs on the GPU."""
+        if not self._graph:
+            raise RuntimeError("call capture() first")
+        if getattr(self, "_static_u8", None) is None:
+            self._static_u8 = tuple(torch.empty(t.shape, dtype=torch.uint8, device=self.device) for t in (x8, m8, y8))
+        for dev8, src, dst in zip(self._static_u8, (x8, m8, y8), self._static):
+            dev8.copy_(src, non_blocking=True)
+            ops.u8_to_nchw(dev8, out=dst)
+        return self.replay()
+
     def loss_dict(self, losses=None):
         v = (self.losses if losses is None else losses).detach().cpu().tolist()
         d = dict(zip(SLOTS, v))

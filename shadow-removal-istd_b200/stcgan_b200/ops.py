@@ -313,6 +313,17 @@ def float2uint_hwc(x_nchw):
     return out
 
 
+def u8_to_nchw(img_u8, out=None):
+    """uint8 [N,H,W,C] (decoded images as cv2 gives them) -> float32 [N,C,H,W] in [-1,1]: the dataset transform on the GPU."""
+    _need_cuda(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 4
+    n, h, w, c = img_u8.shape
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=img_u8.device)
+    check(_lib.load().stcgan_u8_hwc_to_nchw_f32(img_u8.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "stcgan_u8_hwc_to_nchw_f32")
+    return out
+
+
 def float2uint(x):
     assert x.dtype == torch.float32 and x.is_contiguous()
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)

@@ -253,6 +253,19 @@ def test_float2uint_bit_exact(cuda, lib, golden):
     assert np.array_equal(ops.float2uint_hwc(pre).cpu().numpy(), exp)
 
 
+def test_uint8_input_transform_is_bit_exact(cuda, lib):
+    """GPU-side dataset transform == numpy float32 arithmetic of src/utils.py:60-62 + src/dataset.py:152, all 256 levels."""
+    from stcgan_b200 import ops
+    rs = np.random.RandomState(1)
+    img = rs.randint(0, 256, size=(2, 9, 13, 3), dtype=np.uint8)
+    img[0, 0, :, 0] = np.arange(13) * 21 % 256
+    img.reshape(-1)[:256] = np.arange(256, dtype=np.uint8)
+    ref = ((img.astype(np.float32) / 255).transpose(0, 3, 1, 2) - 0.5) * 2
+    assert ref.dtype == np.float32
+    got = ops.u8_to_nchw(torch.from_numpy(img).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
 def test_layout_kernels(cuda, lib):
     from stcgan_b200 import ops
     a = torch.randn(2, 3, 9, 11, device=cuda); b = torch.randn(2, 1, 9, 11, device=cuda); c = torch.randn(2, 3, 9, 11, device=cuda)
