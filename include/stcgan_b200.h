@@ -221,8 +221,10 @@ typedef struct stcgan_adam_tensor {
   float* p; const float* g; float* m; float* v;
   int64_t n;
   int32_t d0, d1;     /* packed-gradient dims, 0 = gradient in parameter layout */
-  void* p1; void* p2; /* optional (both or neither; needs d0 % 16 == 0 and d1 % 16 == 0): bf16 tap-major copies
-                         P1[t][d0][d1], P2[t][d1][d0] refreshed from the updated parameters in the same pass */
+  void* p1; void* p2; /* optional (both or neither; needs d0 % T == 0 and d1 % T == 0 with T = stcgan_adam_tile(), and
+                         16-byte aligned p, g, m, v, p1, p2): bf16 tap-major copies P1[t][d0][d1], P2[t][d1][d0] refreshed
+                         from the updated parameters in the same pass.  Such a tensor is covered by (d0/T)*(d1/T) blocks
+                         (chunk = tile index, d1-tiles fastest) instead of ceil(n / stcgan_adam_chunk()) */
 } stcgan_adam_tensor;
 /* the table lives in DEVICE memory (built once); blocks[] maps each CUDA block to (tensor, chunk).
  * dev_hyper is a DEVICE array of 8 floats, in/out: {lr, beta1, beta2, eps, grad_scale, steps_done, -, -}.
@@ -233,6 +235,8 @@ int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blo
                      float* dev_hyper, void* stream);
 /* elements per block chunk used by stcgan_adam_step (host helper for building dev_blocks) */
 int stcgan_adam_chunk(void);
+/* tile edge T (in (d0, d1) pairs) of tensors whose packed bf16 copies are refreshed by stcgan_adam_step */
+int stcgan_adam_tile(void);
 
 /* ---- inference post-processing ------------------------------------------------------------------------
  * replaces `*0.5+0.5` (src/cgan.py:441-442) + utils.float2uint (src/utils.py:65-67) + CHW->HWC transpose

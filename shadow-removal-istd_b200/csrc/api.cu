@@ -1,8 +1,15 @@
+#include <cstdlib>
 // extern "C" surface of libstcgan_b200.so (see include/stcgan_b200.h for the contract).
 #include "common.cuh"
 
 namespace stcgan {
 int64_t g_launches = 0;
+
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STCGAN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 
 // tapconv_ffma.cu
 int tapconv_ffma(const Geom& g, int dtype, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
@@ -231,6 +238,7 @@ int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blo
 }
 
 int stcgan_adam_chunk(void) { return 256 * 16; }
+int stcgan_adam_tile(void) { return 32; }
 
 int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream) {
   STCGAN_REQUIRE(nchw && out_nhwc);

@@ -84,6 +84,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const T* __restrict__ y, long long P, int C, int ld, double* __restrict__ acc,
                 int cv, int rows, int want_sq) {
+  pdl_prologue();
   extern __shared__ float red[];   // [rows][cv*8] x2
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool active = tr < rows;
@@ -135,6 +136,7 @@ bn_stats_kernel(const T* __restrict__ y, long long P, int C, int ld, double* __r
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ g, long long P, int C, int ld, float* __restrict__ out, int cc, int rows) {
+  pdl_prologue();
   __shared__ float red[256];
   const int tc = threadIdx.x % cc, tr = threadIdx.x / cc;
   for (int c0 = 0; c0 < C; c0 += cc) {
@@ -161,6 +163,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, long long P, 
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ rmean, float* __restrict__ rvar, float momentum, float eps,
                                    int training, float* __restrict__ mean_invstd, float* __restrict__ scale_shift) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, invstd;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(256)
 bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const float* __restrict__ ss,
                     int HC, int WC, long long PC, T* __restrict__ o1, int ld1, int act1,
                     T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
+  pdl_prologue();
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   if (tr >= rows) return;
   const float slope1 = act_slope(act1), slope2 = act_slope(act2);
@@ -281,6 +285,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
                      const float* __restrict__ ss, const float* __restrict__ mi, int HC, int WC,
                      const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
                      double* __restrict__ acc, int cv, int rows) {
+  pdl_prologue();
   extern __shared__ float red[];
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool active = tr < rows;
@@ -332,6 +337,7 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
                     const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
                     const double* __restrict__ acc, T* __restrict__ dy, int lddy,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int cv, int rows) {
+  pdl_prologue();
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool has_bn = ss != nullptr;
   const bool two = g2 != nullptr;
@@ -412,7 +418,7 @@ template <typename T>
 static int bn_stats_t(const void* y, long long P, int C, int ld, double* acc, int want_sq, cudaStream_t st) {
   const RowMap m = row_map(C);
   const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
-  bn_stats_kernel<T><<<stream_grid(P, m.rows * 8, bn_stats_kernel<T>, smem, 2), 256, smem, st>>>(static_cast<const T*>(y), P, C, ld, acc, m.cv, m.rows, want_sq);
+  launch_k(bn_stats_kernel<T>, stream_grid(P, m.rows * 8, bn_stats_kernel<T>, smem, 2), 256, smem, st, static_cast<const T*>(y), P, C, ld, acc, m.cv, m.rows, want_sq);
   return finish_launch();
 }
 
@@ -426,7 +432,7 @@ int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, 
 int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float momentum, float eps, int training, float* mean_invstd, float* scale_shift, cudaStream_t st) {
   if (!training && (!rmean || !rvar)) return STCGAN_EINVAL;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(acc, P, C, gamma, beta, rmean, rvar, momentum, eps, training,
+  launch_k(bn_finalize_kernel, (C + 127) / 128, 128, 0, st, acc, P, C, gamma, beta, rmean, rvar, momentum, eps, training,
                                                       mean_invstd, scale_shift);
   return finish_launch();
 }
@@ -444,12 +450,10 @@ int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, 
   if (PC == 0) return 0;
   const RowMap m = row_map(C);
   if (dtype == STCGAN_F32)
-    bn_act_apply_kernel<float><<<stream_grid(PC, m.rows * 4, bn_act_apply_kernel<float>, 0), 256, 0, st>>>(
-        static_cast<const float*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
+    launch_k(bn_act_apply_kernel<float>, stream_grid(PC, m.rows * 4, bn_act_apply_kernel<float>, 0), 256, 0, st, static_cast<const float*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
         static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
   else
-    bn_act_apply_kernel<__nv_bfloat16><<<stream_grid(PC, m.rows * 4, bn_act_apply_kernel<__nv_bfloat16>, 0), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
+    launch_k(bn_act_apply_kernel<__nv_bfloat16>, stream_grid(PC, m.rows * 4, bn_act_apply_kernel<__nv_bfloat16>, 0), 256, 0, st, static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
         static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
   return finish_launch();
 }
@@ -464,12 +468,10 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
   const RowMap m = row_map(C);
   const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
   if (dtype == STCGAN_F32)
-    bn_bwd_reduce_kernel<float><<<stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 2), 256, smem, st>>>(
-        static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
+    launch_k(bn_bwd_reduce_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 2), 256, smem, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
         static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 2), 256, smem, st>>>(
-        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
+    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 2), 256, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
         act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
   return finish_launch();
 }
@@ -486,12 +488,10 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
   if (P == 0) return 0;
   const RowMap m = row_map(C);
   if (dtype == STCGAN_F32)
-    bn_bwd_apply_kernel<float><<<stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<float>, 0), 256, 0, st>>>(
-        static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
+    launch_k(bn_bwd_apply_kernel<float>, stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<float>, 0), 256, 0, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
         act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<__nv_bfloat16>, 0), 256, 0, st>>>(
-        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
+    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<__nv_bfloat16>, 0), 256, 0, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
         static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
         static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
   return finish_launch();
@@ -502,9 +502,9 @@ int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cud
   const int cc = C < 256 ? C : 256, rows = 256 / cc;
   long long b = (P + rows * 8 - 1) / (rows * 8); if (b > 148 * 8) b = 148 * 8; if (b < 1) b = 1;
   if (dtype == STCGAN_F32)
-    colsum_kernel<float><<<(unsigned)b, 256, 0, st>>>(static_cast<const float*>(g), P, C, ld, out, cc, rows);
+    launch_k(colsum_kernel<float>, (unsigned)b, 256, 0, st, static_cast<const float*>(g), P, C, ld, out, cc, rows);
   else
-    colsum_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), P, C, ld, out, cc, rows);
+    launch_k(colsum_kernel<__nv_bfloat16>, (unsigned)b, 256, 0, st, static_cast<const __nv_bfloat16*>(g), P, C, ld, out, cc, rows);
   return finish_launch();
 }
 

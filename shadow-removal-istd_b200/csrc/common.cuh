@@ -18,6 +18,32 @@ inline int finish_launch() {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+// Programmatic dependent launch (PDL): every kernel of this library is launched with the programmatic-stream-serialization
+// attribute, signals `launch_dependents` as its first instruction and executes `griddepcontrol.wait` before its first global
+// memory access.  The next kernel's CTAs therefore become resident while the last wave of this one is still running, run
+// their prologue (barrier init, TMEM allocation, descriptor prefetch) and start the moment this grid has completed and
+// flushed -- the launch gap and the prologue disappear from the critical path; the data dependency is untouched because
+// nothing is read or written before the wait.  Works in plain streams and under CUDA-graph capture (kernel -> kernel edges
+// become programmatic edges).  STCGAN_PDL=0 turns the attribute off (the device instructions are then no-ops).
+int pdl_enabled();
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const int on = pdl_enabled();
+  cfg.attrs = on ? attr : nullptr;
+  cfg.numAttrs = on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through finish_launch()
+}
+
 #define STCGAN_REQUIRE(cond) do { if (!(cond)) return STCGAN_EINVAL; } while (0)
 
 // ---------------------------------------------------------------------------------------------

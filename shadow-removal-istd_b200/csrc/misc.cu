@@ -10,6 +10,7 @@ namespace stcgan {
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, int D0, int D1, T* __restrict__ p1, T* __restrict__ p2) {
+  pdl_prologue();
   __shared__ float tile[16][32 * 16 + 1];   // [d0][d1*16 + t]
   const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 32;
   // load: rows of 32*16 contiguous floats per d0
@@ -39,9 +40,9 @@ int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, c
   if (D0 <= 0 || D1 <= 0) return STCGAN_EINVAL;
   dim3 grid((D1 + 31) / 32, (D0 + 15) / 16);
   if (dtype == STCGAN_F32)
-    pack_weight_kernel<float><<<grid, 256, 0, st>>>(w, D0, D1, static_cast<float*>(p1), static_cast<float*>(p2));
+    launch_k(pack_weight_kernel<float>, grid, 256, 0, st, w, D0, D1, static_cast<float*>(p1), static_cast<float*>(p2));
   else
-    pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, D0, D1, static_cast<__nv_bfloat16*>(p1),
+    launch_k(pack_weight_kernel<__nv_bfloat16>, grid, 256, 0, st, w, D0, D1, static_cast<__nv_bfloat16*>(p1),
                                                             static_cast<__nv_bfloat16*>(p2));
   return finish_launch();
 }
@@ -52,6 +53,7 @@ int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, c
 //   pack_weight_pad16: Wp[t][r][k], r < 16 (zero rows for r >= Nn), (n, k) = (d0, d1) if n_is_d0 else (d1, d0)
 __global__ void __launch_bounds__(256)
 pack_weight_thin_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d0, int flip, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int Nn = n_is_d0 ? D0 : D1, C = n_is_d0 ? D1 : D0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Nn * 128) return;
@@ -67,6 +69,7 @@ pack_weight_thin_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d0
 
 __global__ void __launch_bounds__(256)
 pack_weight_pad16_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d0, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int Nn = n_is_d0 ? D0 : D1, K = n_is_d0 ? D1 : D0;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 16LL * 16 * K) return;
@@ -82,7 +85,7 @@ pack_weight_pad16_kernel(const float* __restrict__ w, int D0, int D1, int n_is_d
 int pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, cudaStream_t st) {
   const int Nn = n_is_d0 ? D0 : D1, C = n_is_d0 ? D1 : D0;
   if (C > 8 || Nn < 1) return STCGAN_EINVAL;
-  pack_weight_thin_kernel<<<(Nn * 128 + 255) / 256, 256, 0, st>>>(w, D0, D1, n_is_d0, flip, static_cast<__nv_bfloat16*>(out));
+  launch_k(pack_weight_thin_kernel, (Nn * 128 + 255) / 256, 256, 0, st, w, D0, D1, n_is_d0, flip, static_cast<__nv_bfloat16*>(out));
   return finish_launch();
 }
 
@@ -90,13 +93,14 @@ int pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, cu
   const int Nn = n_is_d0 ? D0 : D1, K = n_is_d0 ? D1 : D0;
   if (Nn > 16 || Nn < 1) return STCGAN_EINVAL;
   const long long total = 16LL * 16 * K;
-  pack_weight_pad16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, D0, D1, n_is_d0, static_cast<__nv_bfloat16*>(out));
+  launch_k(pack_weight_pad16_kernel, (unsigned)((total + 255) / 256), 256, 0, st, w, D0, D1, n_is_d0, static_cast<__nv_bfloat16*>(out));
   return finish_launch();
 }
 
 // G[t][d0][d1] -> grad[d0][d1][16]
 __global__ void __launch_bounds__(256)
 unpack_grad_kernel(const float* __restrict__ g, int D0, int D1, float* __restrict__ grad, int accumulate) {
+  pdl_prologue();
   __shared__ float tile[16][32 * 8 + 1];   // [t][d0_local*32 + d1_local], 8 d0 x 32 d1 per block
   const int a0 = blockIdx.y * 8, b0 = blockIdx.x * 32;
   for (int i = threadIdx.x; i < 16 * 256; i += 256) {
@@ -119,7 +123,7 @@ unpack_grad_kernel(const float* __restrict__ g, int D0, int D1, float* __restric
 int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cudaStream_t st) {
   if (D0 <= 0 || D1 <= 0) return STCGAN_EINVAL;
   dim3 grid((D1 + 31) / 32, (D0 + 7) / 8);
-  unpack_grad_kernel<<<grid, 256, 0, st>>>(g, D0, D1, grad, accumulate);
+  launch_k(unpack_grad_kernel, grid, 256, 0, st, g, D0, D1, grad, accumulate);
   return finish_launch();
 }
 
@@ -130,6 +134,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pack_input_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
                   const float* __restrict__ s2, int c2, int N, int H, int W, int border, T* __restrict__ out, int Cpad) {
+  pdl_prologue();
   const int HP = H + 2 * border, WP = W + 2 * border;
   const long long HW = (long long)H * W, P = (long long)N * HP * WP;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -148,16 +153,54 @@ pack_input_kernel(const float* __restrict__ s0, int c0, const float* __restrict_
   }
 }
 
+// bf16, 8 channels per pixel (the zero-bordered thin-layer input): one 16-byte store per pixel, all source loads of a
+// pixel issued before any conversion
+__global__ void __launch_bounds__(256)
+pack_input8_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
+                   const float* __restrict__ s2, int c2, int N, int H, int W, int border, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
+  const int HP = H + 2 * border, WP = W + 2 * border;
+  const long long HW = (long long)H * W, P = (long long)N * HP * WP;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(p % WP); const long long t = p / WP;
+    const int yp = (int)(t % HP); const long long n = t / HP;
+    const int yy = yp - border, xx = xp - border;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const long long r = (long long)yy * W + xx;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float* src = c < c0 ? s0 + (n * c0 + c) * HW : c < c0 + c1 ? s1 + (n * c1 + (c - c0)) * HW
+                         : c < c0 + c1 + c2 ? s2 + (n * c2 + (c - c0 - c1)) * HW : nullptr;
+        if (src) v[c] = __ldg(src + r);
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out + p * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 int pack_input(int dtype, const float* s0, int c0, const float* s1, int c1, const float* s2, int c2,
                int N, int H, int W, int border, void* out, int Cpad, cudaStream_t st) {
   if (c0 + c1 + c2 > Cpad || c0 < 0 || c1 < 0 || c2 < 0 || border < 0) return STCGAN_EINVAL;
   const long long P = (long long)N * (H + 2 * border) * (W + 2 * border);
   if (P == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  if (dtype == STCGAN_BF16 && Cpad == 8 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    launch_k(pack_input8_kernel, (unsigned)b, 256, 0, st, s0, c0, s1, c1, s2, c2, N, H, W, border, static_cast<__nv_bfloat16*>(out));
+    return finish_launch();
+  }
   if (dtype == STCGAN_F32)
-    pack_input_kernel<float><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, H, W, border, static_cast<float*>(out), Cpad);
+    launch_k(pack_input_kernel<float>, (unsigned)b, 256, 0, st, s0, c0, s1, c1, s2, c2, N, H, W, border, static_cast<float*>(out), Cpad);
   else
-    pack_input_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(s0, c0, s1, c1, s2, c2, N, H, W, border,
+    launch_k(pack_input_kernel<__nv_bfloat16>, (unsigned)b, 256, 0, st, s0, c0, s1, c1, s2, c2, N, H, W, border,
                                                                   static_cast<__nv_bfloat16*>(out), Cpad);
   return finish_launch();
 }
@@ -166,6 +209,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 unpack_input_grad_kernel(const T* __restrict__ g, int N, long long HW, int ldg, int coff, int cn,
                          float* __restrict__ grad, int accumulate) {
+  pdl_prologue();
   const long long P = (long long)N * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long n = p / HW, r = p % HW;
@@ -183,9 +227,9 @@ int unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, in
   if (P == 0 || cn == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
   if (dtype == STCGAN_F32)
-    unpack_input_grad_kernel<float><<<(unsigned)b, 256, 0, st>>>(static_cast<const float*>(g), N, HW, ldg, coff, cn, grad, accumulate);
+    launch_k(unpack_input_grad_kernel<float>, (unsigned)b, 256, 0, st, static_cast<const float*>(g), N, HW, ldg, coff, cn, grad, accumulate);
   else
-    unpack_input_grad_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, HW, ldg,
+    launch_k(unpack_input_grad_kernel<__nv_bfloat16>, (unsigned)b, 256, 0, st, static_cast<const __nv_bfloat16*>(g), N, HW, ldg,
                                                                          coff, cn, grad, accumulate);
   return finish_launch();
 }
@@ -194,6 +238,7 @@ int unpack_input_grad(int dtype, const void* g, int N, int H, int W, int ldg, in
 template <typename T, bool TO_NCHW>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const void* __restrict__ src, void* __restrict__ dst, long long HW, int C, int ld) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const long long n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32; const int c0 = blockIdx.y * 32;
@@ -227,8 +272,8 @@ int nhwc_to_nchw(int dtype, const void* x, int N, int H, int W, int C, int ld, f
   const long long HW = (long long)H * W;
   if (N == 0 || HW == 0 || C == 0) return 0;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
-  if (dtype == STCGAN_F32) transpose_kernel<float, true><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
-  else transpose_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  if (dtype == STCGAN_F32) launch_k(transpose_kernel<float, true>, grid, 256, 0, st, x, out, HW, C, ld);
+  else launch_k(transpose_kernel<__nv_bfloat16, true>, grid, 256, 0, st, x, out, HW, C, ld);
   return finish_launch();
 }
 
@@ -236,8 +281,8 @@ int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* ou
   const long long HW = (long long)H * W;
   if (N == 0 || HW == 0 || C == 0) return 0;
   dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
-  if (dtype == STCGAN_F32) transpose_kernel<float, false><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
-  else transpose_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(x, out, HW, C, ld);
+  if (dtype == STCGAN_F32) launch_k(transpose_kernel<float, false>, grid, 256, 0, st, x, out, HW, C, ld);
+  else launch_k(transpose_kernel<__nv_bfloat16, false>, grid, 256, 0, st, x, out, HW, C, ld);
   return finish_launch();
 }
 
@@ -245,6 +290,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 out_act_bwd_kernel(int act, const float* __restrict__ o, const float* __restrict__ d, int N, int H, int W, int C,
                    int border, T* __restrict__ g, int ldg) {
+  pdl_prologue();
   const int HP = H + 2 * border, WP = W + 2 * border;
   const long long HW = (long long)H * W, P = (long long)N * HP * WP;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
@@ -266,13 +312,50 @@ out_act_bwd_kernel(int act, const float* __restrict__ o, const float* __restrict
   }
 }
 
+// bf16, bordered 8-channel gradient (thin tensor-core layers): one 16-byte store per pixel
+__global__ void __launch_bounds__(256)
+out_act_bwd8_kernel(int act, const float* __restrict__ o, const float* __restrict__ d, int N, int H, int W, int C,
+                    int border, __nv_bfloat16* __restrict__ g) {
+  pdl_prologue();
+  const int HP = H + 2 * border, WP = W + 2 * border;
+  const long long HW = (long long)H * W, P = (long long)N * HP * WP;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(p % WP); const long long t = p / WP;
+    const int yp = (int)(t % HP); const long long n = t / HP;
+    const int yy = yp - border, xx = xp - border;
+    float gv[8], ov[8], dv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { gv[c] = 0.f; ov[c] = 0.f; dv[c] = 0.f; }
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const long long r = (long long)yy * W + xx;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) { ov[c] = __ldg(o + (n * C + c) * HW + r); dv[c] = __ldg(d + (n * C + c) * HW + r); }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        gv[c] = act == STCGAN_ACT_TANH ? dv[c] * (1.f - ov[c] * ov[c]) : act == STCGAN_ACT_SIGMOID ? dv[c] * ov[c] * (1.f - ov[c]) : dv[c];
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(gv[2 * e], gv[2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(g + p * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, int border, void* g, int ldg,
                 cudaStream_t st) {
   const long long P = (long long)N * (H + 2 * border) * (W + 2 * border);
   if (P == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  if (dtype == STCGAN_F32) out_act_bwd_kernel<float><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, H, W, C, border, static_cast<float*>(g), ldg);
-  else out_act_bwd_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, st>>>(act, o, d, N, H, W, C, border, static_cast<__nv_bfloat16*>(g), ldg);
+  if (dtype == STCGAN_BF16 && border > 0 && ldg == 8 && C <= 8 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    launch_k(out_act_bwd8_kernel, (unsigned)b, 256, 0, st, act, o, d, N, H, W, C, border, static_cast<__nv_bfloat16*>(g));
+    return finish_launch();
+  }
+  if (dtype == STCGAN_F32) launch_k(out_act_bwd_kernel<float>, (unsigned)b, 256, 0, st, act, o, d, N, H, W, C, border, static_cast<float*>(g), ldg);
+  else launch_k(out_act_bwd_kernel<__nv_bfloat16>, (unsigned)b, 256, 0, st, act, o, d, N, H, W, C, border, static_cast<__nv_bfloat16*>(g), ldg);
   return finish_launch();
 }
 
@@ -291,6 +374,7 @@ constexpr int LOSS_ELEMS_PER_BLOCK = 256 * 8;
 
 __global__ void __launch_bounds__(256)
 fused_loss_kernel(const LossTerms lt, float* __restrict__ loss_out) {
+  pdl_prologue();
   __shared__ float red[8];
   int ti = 0;
   while (ti + 1 < lt.n && (long long)blockIdx.x >= lt.first_block[ti + 1]) ++ti;
@@ -346,7 +430,7 @@ int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaS
     nb += (terms[i].n + LOSS_ELEMS_PER_BLOCK - 1) / LOSS_ELEMS_PER_BLOCK;
   }
   lt.first_block[nterms] = nb;
-  fused_loss_kernel<<<(unsigned)nb, 256, 0, st>>>(lt, loss_out);
+  launch_k(fused_loss_kernel, (unsigned)nb, 256, 0, st, lt, loss_out);
   return finish_launch();
 }
 
@@ -354,7 +438,11 @@ int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaS
 // multi-tensor Adam (torch.optim.Adam semantics: eps added after sqrt(v_hat); no weight decay / amsgrad)
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // ---------------------------------------------------------------------------------------------
-constexpr int ADAM_CHUNK = 256 * 16;   // elements per block
+constexpr int ADAM_CHUNK = 256 * 16;   // elements per block (plain / untiled tensors)
+constexpr int ADAM_TILE = 32;          // tiled tensors: one block = 32 x 32 (d0, d1) pairs x 16 taps
+constexpr int ADAM_G_PITCH = 17;       // floats per pair in the staged gradient tile (odd: conflict-free scalar access)
+constexpr int ADAM_W_PITCH = 40;       // bf16 per row of the staged packed-weight tile (16-byte aligned rows)
+constexpr int ADAM_SMEM = ADAM_TILE * ADAM_TILE * ADAM_G_PITCH * 4 + 16 * ADAM_TILE * ADAM_W_PITCH * 2;
 
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,
                                             float step_size, float inv_bc2_sqrt) {
@@ -364,77 +452,100 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
   p = p - step_size * (m / denom);
 }
 
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {   // read-once data: do not keep it in L1
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restrict__ blocks,
             const float* __restrict__ hyper) {
-  __shared__ __nv_bfloat16 tile[16][16][18];   // [tap][d1 local][d0 local (+2 pad)] for the transposed packed copy
+  pdl_prologue();
+  extern __shared__ __align__(16) uint8_t adam_smem[];
   const float step_size = hyper[6], inv_bc2_sqrt = hyper[7], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3],
               grad_scale = hyper[4];
   const int ti = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
   const stcgan_adam_tensor t = table[ti];
   const long long base = (long long)chunk * ADAM_CHUNK;
-  if (t.d0 > 0) {
-    // packed gradients G[tap][d0][d1]: one thread owns one (d0,d1) pair = 16 contiguous parameters (64 B).
-    // If the tensor also wants its bf16 tap-major copies refreshed (p1/p2 != NULL, d0 and d1 multiples of 16), a block
-    // covers a 16 x 16 tile of pairs so that P1[t][d0][d1] and the transposed P2[t][d1][d0] are written in 32-byte runs.
+  if (t.d0 > 0 && t.p1 != nullptr) {
+    // ---- tiled: packed gradients G[tap][d0][d1], parameters [d0][d1][16], bf16 copies P1[tap][d0][d1], P2[tap][d1][d0].
+    // Every global access of the block is a run of >= 64 contiguous bytes: the gradient tile and the two bf16 tiles go
+    // through shared memory, p / m / v stream as float4 with consecutive threads on consecutive addresses.
+    float* g_s = reinterpret_cast<float*>(adam_smem);                                    // [32*32 pairs][17]
+    __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(adam_smem + ADAM_TILE * ADAM_TILE * ADAM_G_PITCH * 4);   // [16][32][40]
     const long long plane = (long long)t.d0 * t.d1;
-    const bool tiled = t.p1 != nullptr;
-    int i0 = 0, i1 = 0, td0 = 0, td1 = 0;
-    long long r;
-    if (tiled) {
-      const int tiles1 = t.d1 / 16;
-      td0 = (chunk / tiles1) * 16; td1 = (chunk % tiles1) * 16;
-      i0 = threadIdx.x / 16; i1 = threadIdx.x % 16;
-      r = (long long)(td0 + i0) * t.d1 + td1 + i1;
-    } else {
-      r = base / 16 + threadIdx.x;
-      if (r >= plane) return;
+    const int tiles1 = t.d1 / ADAM_TILE;
+    const int td0 = (chunk / tiles1) * ADAM_TILE, td1 = (chunk % tiles1) * ADAM_TILE;
+    // phase 1: gradient tile, 128-byte rows per (tap, d0)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < 16 * ADAM_TILE * (ADAM_TILE / 4); i += 256) {
+      const int tap = i / (ADAM_TILE * 8), r0 = (i / 8) % ADAM_TILE, c4 = (i % 8) * 4;
+      const float4 g = ldg_stream4(t.g + (long long)tap * plane + (long long)(td0 + r0) * t.d1 + td1 + c4);
+      float* d = g_s + (r0 * ADAM_TILE + c4) * ADAM_G_PITCH + tap;
+      d[0] = g.x; d[ADAM_G_PITCH] = g.y; d[2 * ADAM_G_PITCH] = g.z; d[3 * ADAM_G_PITCH] = g.w;
     }
+    __syncthreads();
+    // phase 2: 32 rows of 32 pairs x 16 parameters = 128 float4 per row; 2 rows per pass, 4 passes in flight
+#pragma unroll 1
+    for (int it = 0; it < 16; it += 4) {
+      float4 p[4], m[4], v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = (it + u) * 256 + threadIdx.x, r0 = idx / 128, f = idx % 128;
+        const long long off = ((long long)(td0 + r0) * t.d1 + td1) * 16 + f * 4;
+        p[u] = ldg_stream4(t.p + off); m[u] = ldg_stream4(t.m + off); v[u] = ldg_stream4(t.v + off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = (it + u) * 256 + threadIdx.x, r0 = idx / 128, f = idx % 128, pair = f / 4, q = f % 4;
+        const long long off = ((long long)(td0 + r0) * t.d1 + td1) * 16 + f * 4;
+        const float* gs = g_s + (r0 * ADAM_TILE + pair) * ADAM_G_PITCH + 4 * q;
+        adam_update(p[u].x, m[u].x, v[u].x, gs[0] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+        adam_update(p[u].y, m[u].y, v[u].y, gs[1] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+        adam_update(p[u].z, m[u].z, v[u].z, gs[2] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+        adam_update(p[u].w, m[u].w, v[u].w, gs[3] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+        *reinterpret_cast<float4*>(t.p + off) = p[u];
+        *reinterpret_cast<float4*>(t.m + off) = m[u];
+        *reinterpret_cast<float4*>(t.v + off) = v[u];
+        __nv_bfloat16* ws = w_s + ((4 * q) * ADAM_TILE + r0) * ADAM_W_PITCH + pair;
+        ws[0] = __float2bfloat16_rn(p[u].x);
+        ws[ADAM_TILE * ADAM_W_PITCH] = __float2bfloat16_rn(p[u].y);
+        ws[2 * ADAM_TILE * ADAM_W_PITCH] = __float2bfloat16_rn(p[u].z);
+        ws[3 * ADAM_TILE * ADAM_W_PITCH] = __float2bfloat16_rn(p[u].w);
+      }
+    }
+    __syncthreads();
+    // phase 3: bf16 tap-major copies, 64-byte runs: P1[tap][d0][d1 0..31], P2[tap][d1][d0 0..31]
+    __nv_bfloat16* p1 = static_cast<__nv_bfloat16*>(t.p1);
+    __nv_bfloat16* p2 = static_cast<__nv_bfloat16*>(t.p2);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < 16 * ADAM_TILE * 4; i += 256) {
+      const int tap = i / (ADAM_TILE * 4), r0 = (i / 4) % ADAM_TILE, ch = i % 4;
+      const uint4 w = *reinterpret_cast<const uint4*>(w_s + (tap * ADAM_TILE + r0) * ADAM_W_PITCH + ch * 8);
+      *reinterpret_cast<uint4*>(p1 + (long long)tap * plane + (long long)(td0 + r0) * t.d1 + td1 + ch * 8) = w;
+    }
+#pragma unroll 2
+    for (int i = threadIdx.x; i < 16 * ADAM_TILE * 4; i += 256) {
+      const int tap = i / (ADAM_TILE * 4), c0 = (i / 4) % ADAM_TILE, ch = i % 4;
+      const uint16_t* src = reinterpret_cast<const uint16_t*>(w_s) + (tap * ADAM_TILE + ch * 8) * ADAM_W_PITCH + c0;
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        w[e] = (uint32_t)src[(2 * e) * ADAM_W_PITCH] | ((uint32_t)src[(2 * e + 1) * ADAM_W_PITCH] << 16);
+      *reinterpret_cast<uint4*>(p2 + ((long long)tap * t.d1 + td1 + c0) * t.d0 + td0 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else if (t.d0 > 0) {
+    // packed gradients without bf16 refresh (thin layers): one thread owns one (d0,d1) pair = 16 contiguous parameters
+    const long long plane = (long long)t.d0 * t.d1;
+    const long long r = base / 16 + threadIdx.x;
+    if (r >= plane) return;
     float* pp = t.p + r * 16; float* pm = t.m + r * 16; float* pv = t.v + r * 16;
-    const bool vec = ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(pm) | reinterpret_cast<uintptr_t>(pv)) & 15) == 0;
-    float pnew[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float p[4], m[4], v[4];
-      if (vec) {
-        const float4 a = *reinterpret_cast<const float4*>(pp + 4 * q), b = *reinterpret_cast<const float4*>(pm + 4 * q),
-                     c = *reinterpret_cast<const float4*>(pv + 4 * q);
-        p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; m[0] = b.x; m[1] = b.y; m[2] = b.z; m[3] = b.w;
-        v[0] = c.x; v[1] = c.y; v[2] = c.z; v[3] = c.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { p[k] = pp[4 * q + k]; m[k] = pm[4 * q + k]; v[k] = pv[4 * q + k]; }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float g = t.g[(long long)(4 * q + k) * plane + r] * grad_scale;
-        adam_update(p[k], m[k], v[k], g, beta1, beta2, eps, step_size, inv_bc2_sqrt);
-        pnew[4 * q + k] = p[k];
-      }
-      if (vec) {
-        *reinterpret_cast<float4*>(pp + 4 * q) = make_float4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<float4*>(pm + 4 * q) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(pv + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { pp[4 * q + k] = p[k]; pm[4 * q + k] = m[k]; pv[4 * q + k] = v[k]; }
-      }
-    }
-    if (tiled) {
-      __nv_bfloat16* p1 = static_cast<__nv_bfloat16*>(t.p1);
-      __nv_bfloat16* p2 = static_cast<__nv_bfloat16*>(t.p2);
-#pragma unroll
-      for (int tap = 0; tap < 16; ++tap) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(pnew[tap]);
-        p1[(long long)tap * plane + r] = h;                       // 16 consecutive d1 per tile row: 32-byte runs
-        tile[tap][i1][i0] = h;
-      }
-      __syncthreads();
-      // transposed copy: thread (j1 = tid / 16, j0 = tid % 16) writes P2[tap][td1 + j1][td0 + j0]
-      const int j1 = threadIdx.x / 16, j0 = threadIdx.x % 16;
-#pragma unroll
-      for (int tap = 0; tap < 16; ++tap)
-        p2[((long long)tap * t.d1 + td1 + j1) * t.d0 + td0 + j0] = tile[tap][j1][j0];
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      float p = pp[k], m = pm[k], v = pv[k];
+      adam_update(p, m, v, t.g[(long long)k * plane + r] * grad_scale, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+      pp[k] = p; pm[k] = m; pv[k] = v;
     }
   } else {
 #pragma unroll 4
@@ -450,6 +561,7 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
 
 // steps_done += 1; bias corrections in double like torch (1 - beta^t)
 __global__ void adam_tick_kernel(float* __restrict__ hyper) {
+  pdl_prologue();
   const float step = hyper[5] + 1.f;
   hyper[5] = step;
   const double bc1 = 1.0 - pow((double)hyper[1], (double)step);
@@ -460,9 +572,15 @@ __global__ void adam_tick_kernel(float* __restrict__ hyper) {
 
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st) {
   if (nblocks <= 0) return STCGAN_EINVAL;
-  adam_tick_kernel<<<1, 1, 0, st>>>(hyper);
+  launch_k(adam_tick_kernel, 1, 1, 0, st, hyper);
   ++g_launches;
-  adam_kernel<<<nblocks, 256, 0, st>>>(table, blocks, hyper);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  launch_k(adam_kernel, nblocks, 256, ADAM_SMEM, st, table, blocks, hyper);
   return finish_launch();
 }
 
@@ -476,12 +594,14 @@ __device__ __forceinline__ uint8_t f2u(float a) {
 
 __global__ void __launch_bounds__(256)
 float2uint_kernel(const float* __restrict__ in, long long n, uint8_t* __restrict__ out) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = f2u(in[i]);
 }
 
 __global__ void __launch_bounds__(256)
 float2uint_hwc_kernel(const float* __restrict__ in, int N, int C, long long HW, uint8_t* __restrict__ out) {
+  pdl_prologue();
   const long long P = (long long)N * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long n = p / HW, r = p % HW;
@@ -496,6 +616,7 @@ float2uint_hwc_kernel(const float* __restrict__ in, int N, int C, long long HW, 
 // followed by src/dataset.py:152 ((s.transpose(2,0,1) - 0.5) * 2), every step rounded to float32 like numpy
 __global__ void __launch_bounds__(256)
 u8_to_nchw_kernel(const uint8_t* __restrict__ in, int N, int C, long long HW, float* __restrict__ out) {
+  pdl_prologue();
   const long long P = (long long)N * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long n = p / HW, r = p % HW;
@@ -510,14 +631,14 @@ int u8_to_nchw(const uint8_t* in, int N, int H, int W, int C, float* out, cudaSt
   const long long HW = (long long)H * W, P = N * HW;
   if (P == 0 || C == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  u8_to_nchw_kernel<<<(unsigned)b, 256, 0, st>>>(in, N, C, HW, out);
+  launch_k(u8_to_nchw_kernel, (unsigned)b, 256, 0, st, in, N, C, HW, out);
   return finish_launch();
 }
 
 int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st) {
   if (n == 0) return 0;
   long long b = (n + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  float2uint_kernel<<<(unsigned)b, 256, 0, st>>>(in, n, out);
+  launch_k(float2uint_kernel, (unsigned)b, 256, 0, st, in, n, out);
   return finish_launch();
 }
 
@@ -525,7 +646,7 @@ int float2uint_hwc(const float* in, int N, int C, int H, int W, uint8_t* out, cu
   const long long HW = (long long)H * W, P = N * HW;
   if (P == 0) return 0;
   long long b = (P + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  float2uint_hwc_kernel<<<(unsigned)b, 256, 0, st>>>(in, N, C, HW, out);
+  launch_k(float2uint_hwc_kernel, (unsigned)b, 256, 0, st, in, N, C, HW, out);
   return finish_launch();
 }
 

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(NT)
 tapconv_ffma_kernel(const Geom g, const T* __restrict__ x, int K, int ldx,
                     const T* __restrict__ wp, const float* __restrict__ bias, int act,
                     void* __restrict__ yv, int Nout, int ldy, int out_nchw_f32) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
 
@@ -111,7 +112,7 @@ static int launch_tapconv_ffma(const Geom& g, const void* x, int K, int ldx, con
   }
   if (maxM == 0 || Nout == 0) return 0;
   dim3 grid((unsigned)((maxM + BM - 1) / BM), (unsigned)((Nout + BN - 1) / BN), (unsigned)g.nclass);
-  tapconv_ffma_kernel<T><<<grid, NT, 0, st>>>(g, static_cast<const T*>(x), K, ldx, static_cast<const T*>(wp), bias,
+  launch_k(tapconv_ffma_kernel<T>, grid, NT, 0, st, g, static_cast<const T*>(x), K, ldx, static_cast<const T*>(wp), bias,
                                               act, y, Nout, ldy, out_nchw_f32);
   return finish_launch();
 }
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(NT)
 tapwgrad_ffma_kernel(int N, int SH, int SW, int D0, int lds, int LH, int LW, int D1, int ldl, int stride,
                      const T* __restrict__ S, const T* __restrict__ L, float* __restrict__ G,
                      int tiles1, long long pix_per_split) {
+  pdl_prologue();
   __shared__ float Ss[BK][BM + 4];   // [pixel][d0]
   __shared__ float Ls[BK][BN + 4];   // [pixel][d1]
 
@@ -215,10 +217,10 @@ int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int
   const unsigned splits = (unsigned)((P + pps - 1) / pps);
   dim3 grid((unsigned)(tiles0 * tiles1), 16, splits);
   if (dtype == STCGAN_F32)
-    tapwgrad_ffma_kernel<float><<<grid, NT, 0, st>>>(N, SH, SW, D0, lds, LH, LW, D1, ldl, stride,
+    launch_k(tapwgrad_ffma_kernel<float>, grid, NT, 0, st, N, SH, SW, D0, lds, LH, LW, D1, ldl, stride,
                                                      static_cast<const float*>(S), static_cast<const float*>(L), G, tiles1, pps);
   else
-    tapwgrad_ffma_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(N, SH, SW, D0, lds, LH, LW, D1, ldl, stride,
+    launch_k(tapwgrad_ffma_kernel<__nv_bfloat16>, grid, NT, 0, st, N, SH, SW, D0, lds, LH, LW, D1, ldl, stride,
                                                              static_cast<const __nv_bfloat16*>(S),
                                                              static_cast<const __nv_bfloat16*>(L), G, tiles1, pps);
   return finish_launch();

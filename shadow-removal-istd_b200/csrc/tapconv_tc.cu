@@ -212,6 +212,7 @@ struct TapGemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192)
 tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
+  pdl_trigger();
   using SM = TapGemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -247,6 +248,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is independent of the preceding kernel; global memory is touched only below
   if (threadIdx.x == 0) DBG_T(1);
 
   if (threadIdx.x == 0) {
@@ -432,6 +434,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tiles, int n_tiles, int total_tiles) {
+  pdl_trigger();
   using SM = PersistSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -459,6 +462,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is independent of the preceding kernel; global memory is touched only below
 
   if (threadIdx.x == 0) {
     // ===== TMA producer =====
@@ -654,6 +658,7 @@ struct PairSmem {
 template <int BN2, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
 tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
+  pdl_trigger();
   using SM = PairSmem<BN2, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -690,6 +695,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
   cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is independent of the preceding kernel; global memory is touched only below
   if (threadIdx.x == 0) DBG_T(1);
 
   if (threadIdx.x == 0) {
@@ -820,6 +826,7 @@ struct WgradSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192)
 tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
+  pdl_trigger();
   using SM = WgradSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -849,6 +856,7 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is independent of the preceding kernel; global memory is touched only below
 
   if (threadIdx.x == 0) {
     const CUtensorMap* lm = &P.lmap[P.tview[tap]];
@@ -1054,7 +1062,7 @@ static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  tapgemm_tc_kernel<BN, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  launch_k(tapgemm_tc_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P);
   return finish_launch();
 }
 
@@ -1069,7 +1077,7 @@ static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_
   }
   const int total = m_tiles * n_tiles * nclass;
   const int grid = total < 148 ? total : 148;
-  tapgemm_tc_persistent_kernel<BN, STAGES><<<grid, 192, SM::TOTAL, st>>>(P, m_tiles, n_tiles, total);
+  launch_k(tapgemm_tc_persistent_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P, m_tiles, n_tiles, total);
   return finish_launch();
 }
 
@@ -1085,7 +1093,7 @@ static int launch_tapgemm_pair_raw(const TapGemmParams& P, dim3 grid, cudaStream
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  tapgemm_tc_pair_kernel<BN2, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  launch_k(tapgemm_tc_pair_kernel<BN2, STAGES>, grid, 192, SM::TOTAL, st, P);
   return finish_launch();
 }
 
@@ -1127,13 +1135,13 @@ static int persistent_mode() {
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
                      __nv_bfloat16* __restrict__ y, int ldy) {
+  pdl_prologue();
   const int quads = Nout / 4;
   const long long total = P * quads;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / quads; const int c = (int)(i % quads) * 4;
     const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
     float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
     const float slope = act_slope(act);
 #pragma unroll
     for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
@@ -1238,7 +1246,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     if (rc) return rc;
     const long long Ppix = (long long)g.N * g.OH * g.OW;
     long long blocks = (Ppix * (Nout / 4) + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
+    launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
     return finish_launch();
   }
   if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
@@ -1332,7 +1340,7 @@ static int launch_wgrad(const WgradParams& P, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  tapwgrad_tc_kernel<BN, STAGES><<<grid, 192, SM::TOTAL, st>>>(P);
+  launch_k(tapwgrad_tc_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P);
   return finish_launch();
 }
 

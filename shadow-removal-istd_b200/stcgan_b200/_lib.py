@@ -70,6 +70,7 @@ SIGNATURES = {
     "stcgan_fused_loss": (_i, [C.POINTER(LossTerm), _i, _p, _p]),
     "stcgan_adam_step": (_i, [_p, _p, _i, _p, _p]),
     "stcgan_adam_chunk": (_i, []),
+    "stcgan_adam_tile": (_i, []),
     "stcgan_float2uint_hwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_float2uint": (_i, [_p, _i64, _p, _p]),
     "stcgan_u8_hwc_to_nchw_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),

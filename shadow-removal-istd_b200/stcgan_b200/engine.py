@@ -106,12 +106,18 @@ class STCGANEngine:
         newg = lambda t: torch.empty_like(t)
         # ================= D phase (cgan.py:278-305) =================
         rt["D1"].zero_grads(); rt["D2"].zero_grads()
-        c1r, w1r = rt["D1"].forward([x, m], True)
+        # every distinct input concatenation (cgan.py:281-289, 321-324) is packed once per step and shared
+        pk_xm = rt["D1"].pack_sources([x, m])
+        c1r, w1r = rt["D1"].forward([x, m], True, packed=pk_xm)
         mp, wg1 = rt["G1"].forward([x], True)
-        c1f, w1f = rt["D1"].forward([x, mp], True)
-        c2r, w2r = rt["D2"].forward([x, m, y], True)
-        yp, wg2 = rt["G2"].forward([x, mp], True)
-        c2f, w2f = rt["D2"].forward([x, mp, yp], True)
+        pk_xmp = rt["D1"].pack_sources([x, mp])
+        c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)
+        pk_xmy = rt["D2"].pack_sources([x, m, y])
+        c2r, w2r = rt["D2"].forward([x, m, y], True, packed=pk_xmy)
+        share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
+        yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
+        pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
+        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)
         self.last = dict(m_pred=mp, y_pred=yp)
         self.losses.zero_()
         d1r, d1f, d2r, d2f = newg(c1r), newg(c1f), newg(c2r), newg(c2f)
@@ -129,10 +135,10 @@ class STCGANEngine:
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
         if not cfg.skip_dead_real_passes:
-            rt["D1"].forward([x, m], True)                    # cgan.py:321 (BatchNorm running-stat side effect only)
-            rt["D2"].forward([x, m, y], True)                 # cgan.py:323
-        c1f, w1f = rt["D1"].forward([x, mp], True)            # cgan.py:322
-        c2f, w2f = rt["D2"].forward([x, mp, yp], True)        # cgan.py:324
+            rt["D1"].forward([x, m], True, packed=pk_xm)      # cgan.py:321 (BatchNorm running-stat side effect only)
+            rt["D2"].forward([x, m, y], True, packed=pk_xmy)  # cgan.py:323
+        c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)        # cgan.py:322
+        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)  # cgan.py:324
         dm, dy, d1f, d2f = newg(mp), newg(yp), newg(c1f), newg(c2f)
         ops.fused_loss([
             dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),

@@ -224,6 +224,23 @@ class _NetRuntimeBase:
     def device(self):
         return self.convs[0].weight.device
 
+    def pack_sources(self, sources):
+        """The torch.cat of cgan.py:281-289,321-324 as ONE packed NHWC tensor: ("b", zero-bordered 8-channel tensor) when
+        the first layer runs on the thin tensor-core path, else ("p", cpad-channel tensor).  The result only depends on the
+        sources, so the engine packs each distinct concatenation once per step and shares it between networks."""
+        self.ensure_packed()
+        first = self.convs[0]
+        if first.thin == "cin":
+            return ("b", ops.pack_input(sources, 8, self.act_dtype, border=1))
+        return ("p%d" % self.cpad, ops.pack_input(sources, self.cpad, self.act_dtype))
+
+    def _packed_input(self, sources, packed):
+        kind, t = packed if packed is not None else self.pack_sources(sources)
+        want = "b" if self.convs[0].thin == "cin" else "p%d" % self.cpad
+        if kind != want:
+            raise ValueError(f"packed input layout {kind!r} does not fit this network (needs {want!r})")
+        return (None, t) if kind == "b" else (t, None)
+
     def ensure_packed(self, force=False):
         for c in self.convs:
             c.ensure_packed(self.act_dtype, force)
@@ -297,19 +314,15 @@ class GeneratorRuntime(_NetRuntimeBase):
             s.append(self.downs[k - 1].out_size(ph, pw))
         return s
 
-    def forward(self, sources, training):
+    def forward(self, sources, training, packed=None):
         """sources: list of NCHW fp32 tensors concatenated along channels (the torch.cat of cgan.py:286).
-        Returns (out NCHW fp32, workspace)."""
+        `packed`: result of pack_sources(sources), if the caller already has it.  Returns (out NCHW fp32, workspace)."""
         self.ensure_packed()
         dt, dev, L = self.act_dtype, self.device(), self.L
-        thin_in = self.downs[0].thin == "cin"
         n, _, h, w = sources[0].shape
-        if thin_in:          # zero-bordered 8-channel input: the thin-K tensor-core path reads its windows from it
-            inp_b = ops.pack_input(sources, 8, dt, border=1)
-            inp = None
-        else:
-            inp_b = None
-            inp = ops.pack_input(sources, self.cpad, dt)
+        # thin first layer: zero-bordered 8-channel input, the thin-K tensor-core path reads its windows from it
+        inp, inp_b = self._packed_input(sources, packed)
+        thin_in = inp_b is not None
         s = self.sizes(h, w)
         arena = _BNArena([b.c for b in self.bns], dev)
         if training and self.counters is not None:
@@ -434,15 +447,12 @@ class DiscriminatorRuntime(_NetRuntimeBase):
         self.use_sigmoid = use_sigmoid
         super().__init__(list(convs), [b for b in bns if b is not None], precision)
 
-    def forward(self, sources, training):
+    def forward(self, sources, training, packed=None):
         self.ensure_packed()
         dt, dev = self.act_dtype, self.device()
-        thin_in = self.layers[0].thin == "cin"
         n, _, h, w = sources[0].shape
-        if thin_in:
-            inp_b, inp = ops.pack_input(sources, 8, dt, border=1), None
-        else:
-            inp_b, inp = None, ops.pack_input(sources, self.cpad, dt)
+        inp, inp_b = self._packed_input(sources, packed)
+        thin_in = inp_b is not None
         nl = len(self.layers)
         arena = _BNArena([b.c for b in self.bns], dev)
         if training and self.counters is not None:

@@ -72,6 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _build_table(self, group):
         chunk = _lib.load().stcgan_adam_chunk()
+        tile = _lib.load().stcgan_adam_tile()
         entries, blocks, keep, fused = [], [], [], []
         for p in group["params"]:
             gd = self._grad_of(p)
@@ -87,14 +88,16 @@ class FusedAdam(torch.optim.Optimizer):
             ti = len(entries)
             conv = self._pack_targets.get(id(p))
             p1 = p2 = None
-            if (conv is not None and d0 > 0 and d0 % 16 == 0 and d1 % 16 == 0 and conv.p1 is not None
-                    and conv.p1.dtype == torch.bfloat16):
+            aligned = all(t.data_ptr() % 16 == 0 for t in (p, g, st["exp_avg"], st["exp_avg_sq"]))
+            if (conv is not None and d0 > 0 and d0 % tile == 0 and d1 % tile == 0 and conv.p1 is not None
+                    and conv.p1.dtype == torch.bfloat16 and aligned):
                 p1, p2 = conv.p1.data_ptr(), conv.p2.data_ptr()
                 fused.append(conv)
             entries.append(_lib.AdamTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
                                            st["exp_avg_sq"].data_ptr(), p.numel(), d0, d1, p1, p2))
             keep.append((p, g, st))
-            blocks += [(ti, c) for c in range((p.numel() + chunk - 1) // chunk)]
+            nblk = (d0 // tile) * (d1 // tile) if p1 is not None else (p.numel() + chunk - 1) // chunk
+            blocks += [(ti, c) for c in range(nblk)]
         if not entries:
             return None
         arr = (_lib.AdamTensor * len(entries))(*entries)
