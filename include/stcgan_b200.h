@@ -97,6 +97,16 @@ int stcgan_tapconv(int geom, int dtype, int backend,
                    void* y, int OH, int OW, int Nout, int ldy, int out_nchw_f32,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same convolution with the following BatchNorm's batch statistics fused into the GEMM epilogue (tensor-core backend,
+ * bf16, act == STCGAN_ACT_NONE, Nout % 64 == 0): per output channel the sum and the sum of squares of the bf16-rounded
+ * outputs are added (fp64 atomics) to bn_acc[STCGAN_BN_SLOTS][2][Nout] -- STCGAN_BN_SLOTS partial slots that spread the
+ * atomic traffic; the caller zeroes bn_acc and stcgan_bn_fused_apply sums the slots.  Replaces the separate statistics pass
+ * over the conv output of nn.BatchNorm2d in training mode (stcgan_g.py:88,90; stcgan_d.py:36,45). */
+#define STCGAN_BN_SLOTS 4
+int stcgan_tapconv_bnstats(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp,
+                           void* y, int OH, int OW, int Nout, int ldy, void* workspace, int64_t workspace_bytes,
+                           double* bn_acc, void* stream);
+
 /* weight gradient of the same convolutions:  G[t][d0][d1] += sum_p S[p, d0] * L[win_t(p), d1]
  * S : "small-grid" tensor [N, SH, SW, D0] pitch lds (Conv2d: dY; ConvTranspose2d: the layer input)
  * L : "large-grid" tensor [N, LH, LW, D1] pitch ldl (Conv2d: the layer input; ConvTranspose2d: dY)
@@ -158,6 +168,15 @@ int stcgan_bn_finalize(const double* acc, int64_t P, int C, const float* gamma, 
 int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
                         const float* scale_shift, int HC, int WC,
                         void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
+/* stcgan_bn_finalize + stcgan_bn_act_apply in ONE launch.  training != 0: statistics = sum over the STCGAN_BN_SLOTS slots
+ * of acc[slot][2][C] (stcgan_bn_stats fills slot 0, stcgan_tapconv_bnstats all of them) over `count` values per channel;
+ * training == 0: running statistics.  Writes mean_invstd / scale_shift (for the backward pass), updates the running
+ * statistics (training, NULL = skip) and applies out1 = act1(y*scale+shift) [, out2 = act2(..)] over the crop. */
+int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
+                          const double* acc, int64_t count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float eps, int training,
+                          float* mean_invstd, float* scale_shift, int HC, int WC,
+                          void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
 /* backward, pass 1: dz = g1*act1'(z) + g2*act2'(z) (z = y*scale+shift, zero outside the crop);
  * acc[0][c] += sum dz, acc[1][c] += sum dz*xhat   (fp64, caller zeroes) */
 int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy,

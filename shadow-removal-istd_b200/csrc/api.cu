@@ -18,7 +18,8 @@ int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int
                   const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
 // tapconv_tc.cu
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
-               void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32, float* ws, long long ws_bytes);
+               void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32, float* ws, long long ws_bytes,
+               double* bn_acc);
 int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
                 void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st);
 int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const void* f, int FH, int FW, int Dfat, int ldf,
@@ -39,6 +40,10 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
                      const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
                      float* dgamma, float* dbeta, cudaStream_t st);
 int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cudaStream_t st);
+int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const double* acc, long long count,
+                   const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps, int training,
+                   float* mean_invstd, float* scale_shift, int HC, int WC,
+                   void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st);
 // misc.cu
 int pack_weight(int dtype, const float* w, int D0, int D1, void* p1, void* p2, cudaStream_t st);
 int unpack_grad(const float* g, int D0, int D1, float* grad, int accumulate, cudaStream_t st);
@@ -92,10 +97,32 @@ int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int I
   if (backend == STCGAN_BACKEND_TC) {
     if (dtype != STCGAN_BF16 || out_nchw_f32) return STCGAN_EUNSUPPORTED;
     return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream), 0, nullptr,
-                      static_cast<float*>(workspace), (long long)workspace_bytes);
+                      static_cast<float*>(workspace), (long long)workspace_bytes, nullptr);
   }
   if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
   return tapconv_ffma(g, dtype, x, K, ldx, wp, bias, act, y, Nout, ldy, out_nchw_f32, as_stream(stream));
+}
+
+int stcgan_tapconv_bnstats(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp,
+                           void* y, int OH, int OW, int Nout, int ldy, void* workspace, int64_t workspace_bytes,
+                           double* bn_acc, void* stream) {
+  STCGAN_REQUIRE(x && wp && y && bn_acc);
+  STCGAN_REQUIRE(N >= 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && K > 0 && Nout > 0 && ldx >= K && ldy >= Nout);
+  Geom g;
+  if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
+  if (N == 0) return 0;
+  return tapconv_tc(geom, g, x, K, ldx, wp, nullptr, STCGAN_ACT_NONE, y, Nout, ldy, as_stream(stream), 0, nullptr,
+                    static_cast<float*>(workspace), (long long)workspace_bytes, bn_acc);
+}
+
+int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
+                          const double* acc, int64_t count, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float momentum, float eps, int training,
+                          float* mean_invstd, float* scale_shift, int HC, int WC,
+                          void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && N >= 0 && H > 0 && W > 0 && HC > 0 && WC > 0 && C > 0);
+  return bn_fused_apply(dtype, y, N, H, W, C, ldy, acc, (long long)count, gamma, beta, running_mean, running_var, momentum,
+                        eps, training, mean_invstd, scale_shift, HC, WC, out1, ld1, act1, out2, ld2, act2, as_stream(stream));
 }
 
 int stcgan_tapwgrad(int geom, int dtype, int backend, const void* S, int N, int SH, int SW, int D0, int lds,
@@ -177,7 +204,7 @@ int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K,
   Geom g;
   if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
   if (N == 0) return 0;
-  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32, nullptr, 0);
+  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32, nullptr, 0, nullptr);
 }
 
 int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,

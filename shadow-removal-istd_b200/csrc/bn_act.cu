@@ -241,6 +241,100 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// finalize + apply in one launch: every block derives scale / shift of all channels from the statistics (the sums of
+// STCGAN_BN_SLOTS partial slots, training) or from the running statistics (eval) into shared memory; block 0 also
+// publishes mean / invstd / scale / shift for the backward pass and updates the running statistics.
+// ---------------------------------------------------------------------------------------------
+struct BnFinalize {
+  const double* acc;      // [STCGAN_BN_SLOTS][2][C] (training)
+  long long count;        // values per channel
+  const float* gamma; const float* beta;
+  float* rmean; float* rvar;
+  float momentum, eps;
+  int training;
+  float* mean_invstd; float* scale_shift;   // [2][C] each
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_fused_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const BnFinalize f,
+                      int HC, int WC, long long PC, T* __restrict__ o1, int ld1, int act1,
+                      T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
+  extern __shared__ float ssm[];     // [2][C]: scale, shift
+  pdl_prologue();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, invstd;
+    if (f.training) {
+      double s = 0.0, q = 0.0;
+#pragma unroll
+      for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { s += f.acc[(2 * k) * C + c]; q += f.acc[(2 * k + 1) * C + c]; }
+      const double m = s / (double)f.count;
+      double var = q / (double)f.count - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+      if (blockIdx.x == 0 && f.rmean) {
+        const double unbiased = f.count > 1 ? var * (double)f.count / (double)(f.count - 1) : var;
+        f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * (float)m;
+        f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * (float)unbiased;
+      }
+    } else {
+      mean = f.rmean[c];
+      invstd = 1.f / sqrtf(f.rvar[c] + f.eps);
+    }
+    const float sc = f.gamma[c] * invstd, sh = f.beta[c] - mean * sc;
+    ssm[c] = sc; ssm[C + c] = sh;
+    if (blockIdx.x == 0) {
+      f.mean_invstd[c] = mean; f.mean_invstd[C + c] = invstd;
+      f.scale_shift[c] = sc; f.scale_shift[C + c] = sh;
+    }
+  }
+  __syncthreads();
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  if (tr >= rows) return;
+  const float slope1 = act_slope(act1), slope2 = act_slope(act2);
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = ssm[c0 + i]; sh[i] = ssm[C + c0 + i]; }
+    const long long stride = (long long)gridDim.x * rows;
+    const bool nocrop = HC == H && WC == W;
+    for (long long p0 = (long long)blockIdx.x * rows + tr; p0 < PC; p0 += 4 * stride) {
+      Raw8<T> raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        long long p = p0 + u * stride;
+        if (p >= PC) p = PC - 1;
+        long long src = p;
+        if (!nocrop) {
+          const int w = (int)(p % WC); const long long t = p / WC;
+          const int h = (int)(t % HC); const long long n = t / HC;
+          src = (n * H + h) * W + w;
+        }
+        raw[u].ld(y + src * (long long)ldy + c0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long p = p0 + u * stride;
+        if (p < PC) {
+          Vec8<T> a, b;
+          float yv[8];
+          raw[u].unpack(yv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(yv[i], sc[i], sh[i]);
+            a.v[i] = act_piecewise(z, slope1);
+            b.v[i] = act_piecewise(z, slope2);
+          }
+          a.store(o1 + p * ld1 + c0);
+          if (o2) b.store(o2 + p * ld2 + c0);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 // raw operands of one pixel (8 channels): y, and the incoming gradients (zero outside the crop).  `load` only issues
@@ -455,6 +549,32 @@ int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, 
   else
     launch_k(bn_act_apply_kernel<__nv_bfloat16>, stream_grid(PC, m.rows * 4, bn_act_apply_kernel<__nv_bfloat16>, 0), 256, 0, st, static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, ss, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
         static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
+  return finish_launch();
+}
+
+int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const double* acc, long long count,
+                   const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps, int training,
+                   float* mean_invstd, float* scale_shift, int HC, int WC,
+                   void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st) {
+  if (C % VEC != 0 || C > 2048 || HC > H || WC > W || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, o1, ld1) || !vec_ok(dtype, o2, ld2) || !o1)
+    return STCGAN_EINVAL;
+  if (!gamma || !beta || !mean_invstd || !scale_shift) return STCGAN_EINVAL;
+  if (training ? (!acc || count < 1) : (!rmean || !rvar)) return STCGAN_EINVAL;
+  const long long PC = (long long)N * HC * WC;
+  if (PC == 0) return 0;
+  const RowMap m = row_map(C);
+  BnFinalize f;
+  f.acc = acc; f.count = count; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar;
+  f.momentum = momentum; f.eps = eps; f.training = training; f.mean_invstd = mean_invstd; f.scale_shift = scale_shift;
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if (dtype == STCGAN_F32)
+    launch_k(bn_fused_apply_kernel<float>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<float>, smem), 256, smem, st,
+             static_cast<const float*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
+             static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
+  else
+    launch_k(bn_fused_apply_kernel<__nv_bfloat16>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
+             static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
+             static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
   return finish_launch();
 }
 

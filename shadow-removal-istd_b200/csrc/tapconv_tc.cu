@@ -190,6 +190,10 @@ struct alignas(64) TapGemmParams {
   float* part_out;
   int part_ld;
   long long* dbg;          // optional per-CTA timestamps (8 x int64 per CTA), profiling aid (STCGAN_TC_DEBUG_TIMES)
+  // BatchNorm statistics fused into the epilogue: per output channel sum and sum of squares of the bf16-rounded outputs
+  // (fp32 over the 128 rows of a tile, then fp64 atomics) into bn_acc[slot][2][bn_c], slot = CTA index % STCGAN_BN_SLOTS
+  double* bn_acc;
+  int bn_c;
 };
 
 __device__ __forceinline__ long long gtime() {
@@ -207,6 +211,9 @@ struct TapGemmSmem {
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  // epilogue reuse of the (idle) pipeline smem: bf16 staging tile, then the column-statistics scratch
+  static constexpr int STAT_OFFSET = (TC_BM * (BN * 2 + 16) + 127) / 128 * 128;
+  static_assert(BN < 64 || STAT_OFFSET + 2 * 1024 * 4 <= BAR_OFFSET, "statistics scratch must fit in the pipeline smem");
 };
 
 template <int BN, int STAGES>
@@ -352,7 +359,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
             if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
             f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
             const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            w[e] = valid ? *reinterpret_cast<const uint32_t*>(&h) : 0u;     // rows outside the tensor count as zeros below
           }
           st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
         }
@@ -370,6 +377,41 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         if (pr) {
           const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16);
           *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+        }
+      }
+      if (P.bn_acc) {
+        // BatchNorm statistics of this tile from the staged bf16 values: thread (rg, cg) sums 8 channels over its row
+        // group, the row groups are combined through smem, one fp64 atomic pair per channel and CTA
+        constexpr int CG = BN / 8, RG = 128 / CG, RPG = 128 / RG;
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // all four epilogue warps have staged their rows
+        const int et = threadIdx.x - 64, cg = et % CG, rg = et / CG;
+        float s8[8], q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s8[i] = 0.f; q8[i] = 0.f; }
+        const uint32_t sbase = smem_u32(smem) + (uint32_t)(rg * RPG) * PITCH + cg * 16;
+#pragma unroll 4
+        for (int r = 0; r < RPG; ++r) {
+          const uint4 u = ld_shared_v4(sbase + (uint32_t)r * PITCH);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = __uint_as_float(w4[i] << 16), b = __uint_as_float(w4[i] & 0xffff0000u);
+            s8[2 * i] += a; q8[2 * i] = fmaf(a, a, q8[2 * i]);
+            s8[2 * i + 1] += b; q8[2 * i + 1] = fmaf(b, b, q8[2 * i + 1]);
+          }
+        }
+        float* red = reinterpret_cast<float*>(smem + SM::STAT_OFFSET);      // [2][RG][BN]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { red[rg * BN + cg * 8 + i] = s8[i]; red[RG * BN + rg * BN + cg * 8 + i] = q8[i]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int slot = (int)((blockIdx.x + blockIdx.z) % STCGAN_BN_SLOTS);
+        double* acc = P.bn_acc + (long long)slot * 2 * P.bn_c + n_col0;
+        for (int c = et; c < BN; c += 128) {
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < RG; ++g2) { ts += red[g2 * BN + c]; tq += red[RG * BN + g2 * BN + c]; }
+          atomicAdd(acc + c, (double)ts);
+          atomicAdd(acc + P.bn_c + c, (double)tq);
         }
       }
     } else {
@@ -1134,26 +1176,49 @@ static int persistent_mode() {
 // fp32 split-K partial sums [P][Nout] -> bf16 y (pitch ldy) with bias + activation
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
-                     __nv_bfloat16* __restrict__ y, int ldy) {
+                     __nv_bfloat16* __restrict__ y, int ldy, double* __restrict__ bn_acc) {
   pdl_prologue();
   const int quads = Nout / 4;
-  const long long total = P * quads;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / quads; const int c = (int)(i % quads) * 4;
+  const float slope = act_slope(act);
+  if (bn_acc == nullptr) {
+    const long long total = P * quads;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long p = i / quads; const int c = (int)(i % quads) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
+      float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+      uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
+    }
+    return;
+  }
+  // with BatchNorm statistics (host guarantees quads <= 256 and 256 % quads == 0): a thread keeps one channel quad and
+  // walks down the rows; per-thread fp32 sums of the bf16-rounded outputs, then fp64 atomics into slot blockIdx.x % SLOTS
+  const int qd = threadIdx.x % quads, rr = threadIdx.x / quads, rpb = 256 / quads, c = qd * 4;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p = (long long)blockIdx.x * rpb + rr; p < P; p += (long long)gridDim.x * rpb) {
     const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
     float f[4] = {v.x, v.y, v.z, v.w};
-    const float slope = act_slope(act);
 #pragma unroll
     for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
     const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
     uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
+    const float r[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s4[e] += r[e]; q4[e] = fmaf(r[e], r[e], q4[e]); }
   }
+  double* acc = bn_acc + (long long)(blockIdx.x % STCGAN_BN_SLOTS) * 2 * Nout;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { atomicAdd(acc + c + e, (double)s4[e]); atomicAdd(acc + Nout + c + e, (double)q4[e]); }
 }
 
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
                void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr,
-               float* ws = nullptr, long long ws_bytes = 0) {
+               float* ws = nullptr, long long ws_bytes = 0, double* bn_acc = nullptr) {
+  if (bn_acc && (thin_n || act != STCGAN_ACT_NONE || Nout % 64 != 0)) return STCGAN_EUNSUPPORTED;
   if (K % 64 != 0 || ldx % 8 != 0 || !al16(x) || !al16(wp)) return STCGAN_EUNSUPPORTED;
   if (!thin_n) {
     if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(y)) return STCGAN_EUNSUPPORTED;
@@ -1165,6 +1230,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   TapGemmParams P;
   memset(&P, 0, sizeof(P));
   P.nout_real = Nout; P.y32 = y32;
+  P.bn_acc = bn_acc; P.bn_c = Nout;
   const int n_rows = thin_n ? 16 : Nout;     // rows per tap in the packed weight matrix
   int GH = 0, GW = 0;
   for (int c = 0; c < g.nclass; ++c) {
@@ -1210,7 +1276,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
       if (ksplit > 1) BNsel = bn_s;
     }
   }
-  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 ? 128 : BNsel));
+  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc ? 128 : BNsel));
   if (rc) return rc;
 
   for (int c = 0; c < g.nclass; ++c)
@@ -1240,20 +1306,27 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   if (ksplit > 1) {
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
     if (e != cudaSuccess) return (int)e;
-    P.ksplit = ksplit; P.part_out = ws; P.part_ld = Nout;
+    P.ksplit = ksplit; P.part_out = ws; P.part_ld = Nout; P.bn_acc = nullptr;
     dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)(g.nclass * ksplit));
     rc = BN == 256 ? launch_tapgemm<256, 2>(P, grid, st) : BN == 128 ? launch_tapgemm<128, 3>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
     if (rc) return rc;
     const long long Ppix = (long long)g.N * g.OH * g.OW;
     long long blocks = (Ppix * (Nout / 4) + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
-    launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy);
+    if (bn_acc) {
+      const int quads = Nout / 4;
+      if (quads > 256 || 256 % quads != 0) return STCGAN_EUNSUPPORTED;
+      const int rpb = 256 / quads;
+      blocks = (Ppix + rpb * 4 - 1) / (rpb * 4); if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
+    }
+    P.bn_acc = nullptr;     // (the GEMM launch above already ran; statistics come from the finished sums)
+    launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy, bn_acc);
     return finish_launch();
   }
-  if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
+  if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     return launch_tapgemm_pair<256, 3>(P, m_tiles, Nout / 256, g.nclass, st);
   }
-  if (persistent_mode() == 1 && BN != 256) {
+  if (persistent_mode() == 1 && BN != 256 && !bn_acc) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, g.nclass, st);
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);

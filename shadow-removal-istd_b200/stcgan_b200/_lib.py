@@ -47,6 +47,9 @@ SIGNATURES = {
     "stcgan_launch_count": (_i64, []),
     "stcgan_launch_count_reset": (None, []),
     "stcgan_tapconv": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i64, _p]),
+    "stcgan_tapconv_bnstats": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _p]),
+    "stcgan_bn_fused_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _f, _f, _i, _p, _p, _i, _i,
+                                   _p, _i, _i, _p, _i, _i, _p]),
     "stcgan_tapwgrad": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight": (_i, [_i, _p, _i, _i, _p, _p, _p]),
     "stcgan_unpack_grad": (_i, [_p, _i, _i, _p, _i, _p]),
@@ -103,6 +106,9 @@ def load():
         raise StcganLibraryError("ABI version mismatch")
     _lib = lib
     return lib
+
+
+BN_SLOTS = 4     # STCGAN_BN_SLOTS of include/stcgan_b200.h
 
 
 def check(code: int, what: str = ""):

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BACKEND_FFMA, BACKEND_TC, GEOM_PARITY,
                    GEOM_WIN_S1, GEOM_WIN_S1_FLIP, GEOM_WIN_S2)
 
@@ -95,7 +95,11 @@ class ConvOp:
             return ih - 1, iw - 1
         return ih * 2, iw * 2
 
-    def forward(self, x, oh, ow, *, out=None, out_nchw=None, act=ACT_NONE, use_bias=True, x_bordered=None):
+    def stats_fusable(self):
+        """True if forward() can accumulate the following BatchNorm's batch statistics in its GEMM epilogue."""
+        return self.use_tc and self.thin is None and self.bias is None and ops.tc_eligible_conv(self.cin, self.cout)
+
+    def forward(self, x, oh, ow, *, out=None, out_nchw=None, act=ACT_NONE, use_bias=True, x_bordered=None, bn_acc=None):
         geom = {"conv2": GEOM_WIN_S2, "conv1": GEOM_WIN_S1, "convT": GEOM_PARITY}[self.kind]
         wp = self.p2 if self.kind == "convT" else self.p1
         bias = self.bias.detach() if (self.bias is not None and use_bias) else None
@@ -106,7 +110,7 @@ class ConvOp:
             return out_nchw
         plain = out_nchw is None and act in (ACT_NONE, ACT_LEAKY, ACT_RELU)
         return ops.tapconv(geom, x, wp, self.cout, oh, ow, bias=bias, act=act, out=out, out_nchw=out_nchw,
-                           backend=self._backend_conv(self.cin, self.cout, plain))
+                           backend=self._backend_conv(self.cin, self.cout, plain), bn_acc=bn_acc)
 
     def dgrad(self, g, ih, iw, *, out=None, out8=None, g_bordered=None):
         """gradient w.r.t. the layer input [N, ih, iw, cin] from g = gradient w.r.t. the layer output.
@@ -153,24 +157,26 @@ class BNOp:
         self.ggamma = self.gbeta = None     # fp32 gradient views
         self.shared_counter = False         # True: num_batches_tracked is a view into the runtime's flat counter tensor
 
-    def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE):
-        """stats (training) -> finalize -> apply.  scratch: dict with 'acc' (f64 [2,C]), 'mi', 'ss' (f32 [2,C])."""
+    def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE, stats_done=False):
+        """[stats (training, unless the producing GEMM already accumulated them: stats_done)] -> finalize + apply in one
+        launch.  scratch: dict with 'acc' (f64 [BN_SLOTS,2,C], zeroed), 'mi', 'ss' (f32 [2,C])."""
         m = self.m
         n, h, w, _ = y.shape
         if training:
             if n * h * w <= 1:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size {[n, self.c, h, w]}")
-            ops.bn_stats(y, scratch["acc"])
+            if not stats_done:
+                ops.bn_stats(y, scratch["acc"])          # fills slot 0
             use_running = m.track_running_stats and m.running_mean is not None
-            ops.bn_finalize(scratch["acc"], n * h * w, m.weight.detach(), m.bias.detach(),
-                            m.running_mean if use_running else None, m.running_var if use_running else None,
-                            BN_MOMENTUM if m.momentum is None else m.momentum, m.eps, True, scratch["mi"], scratch["ss"])
+            ops.bn_fused_apply(y, scratch["acc"], n * h * w, m.weight.detach(), m.bias.detach(),
+                               m.running_mean if use_running else None, m.running_var if use_running else None,
+                               BN_MOMENTUM if m.momentum is None else m.momentum, m.eps, True, scratch["mi"], scratch["ss"],
+                               out1, act1, out2, act2)
             if use_running and m.num_batches_tracked is not None and not self.shared_counter:
                 m.num_batches_tracked.add_(1)
         else:
-            ops.bn_finalize(None, n * h * w, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var,
-                            0.0, m.eps, False, scratch["mi"], scratch["ss"])
-        ops.bn_act_apply(y, scratch["ss"], out1, act1, out2, act2)
+            ops.bn_fused_apply(y, None, n * h * w, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var,
+                               0.0, m.eps, False, scratch["mi"], scratch["ss"], out1, act1, out2, act2)
 
     def backward(self, y, scratch, training, g1, act1, g2, act2, dy, want_param_grads, zero_acc=True):
         if zero_acc:
@@ -181,24 +187,26 @@ class BNOp:
 
 
 def _bn_scratch(c, device):
-    return {"acc": torch.zeros((2, c), dtype=torch.float64, device=device),
+    return {"acc": torch.zeros((_lib.BN_SLOTS, 2, c), dtype=torch.float64, device=device),
             "mi": torch.empty((2, c), dtype=torch.float32, device=device),
             "ss": torch.empty((2, c), dtype=torch.float32, device=device)}
 
 
 class _BNArena:
-    """Per-pass BatchNorm scratch for a whole network: ONE zero-fill instead of one per layer."""
+    """Per-pass BatchNorm scratch for a whole network: ONE zero-fill instead of one per layer.  Every layer owns
+    BN_SLOTS x [2, C] fp64 accumulators (forward: partial statistic slots; backward: slot 0 holds the two reductions)."""
 
     def __init__(self, channels, device):
         tot = sum(channels)
-        self.acc = torch.zeros(2 * tot, dtype=torch.float64, device=device)
+        self.acc = torch.zeros(_lib.BN_SLOTS * 2 * tot, dtype=torch.float64, device=device)
         self.f32 = torch.empty(4 * tot, dtype=torch.float32, device=device)
         self.off = 0
 
     def take(self, c):
         o = self.off
         self.off += c
-        return {"acc": self.acc[2 * o:2 * o + 2 * c].view(2, c), "mi": self.f32[4 * o:4 * o + 2 * c].view(2, c),
+        k = _lib.BN_SLOTS * 2
+        return {"acc": self.acc[k * o:k * (o + c)].view(_lib.BN_SLOTS, 2, c), "mi": self.f32[4 * o:4 * o + 2 * c].view(2, c),
                 "ss": self.f32[4 * o + 2 * c:4 * o + 4 * c].view(2, c)}
 
 
@@ -335,16 +343,20 @@ class GeneratorRuntime(_NetRuntimeBase):
         x = None if thin_in else inp[..., :self.cin]
         for k in range(1, L + 1):
             hk, wk = s[k]
-            y = self.downs[k - 1].forward(x, hk, wk, x_bordered=inp_b if k == 1 else None)
+            down = self.downs[k - 1]
+            sc, fuse = None, False
+            if k < L and self.down_bns[k - 1] is not None:
+                sc = arena.take(C[k])
+                fuse = training and down.stats_fusable()
+            y = down.forward(x, hk, wk, x_bordered=inp_b if k == 1 else None, bn_acc=sc["acc"] if fuse else None)
             ws["y"][k] = y
             if k < L:
                 a = new(hk, wk, C[k])
                 cat = new(hk, wk, 2 * C[k])
                 ws["a"][k], ws["cat"][k] = a, cat
                 if self.down_bns[k - 1] is not None:
-                    sc = arena.take(C[k])
                     ws["bn_d"][k] = sc
-                    self.down_bns[k - 1].forward(y, sc, training, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU)
+                    self.down_bns[k - 1].forward(y, sc, training, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU, stats_done=fuse)
                 else:
                     ops.bn_act_apply(y, None, a, ACT_LEAKY, cat[..., :C[k]], ACT_RELU)
                 x = a
@@ -357,12 +369,13 @@ class GeneratorRuntime(_NetRuntimeBase):
         for k in range(L, 1, -1):
             hk, wk = s[k]
             up = self.ups[k - 1]
-            uy = up.forward(x, 2 * hk, 2 * wk)
-            ws["uy"][k] = uy
             sc = arena.take(up.cout)
+            fuse = training and up.stats_fusable()
+            uy = up.forward(x, 2 * hk, 2 * wk, bn_acc=sc["acc"] if fuse else None)
+            ws["uy"][k] = uy
             ws["bn_u"][k] = sc
             dst = ws["cat"][k - 1]
-            self.up_bns[k - 1].forward(uy, sc, training, dst[..., C[k - 1]:], ACT_RELU)   # crops to dst's H, W
+            self.up_bns[k - 1].forward(uy, sc, training, dst[..., C[k - 1]:], ACT_RELU, stats_done=fuse)   # crops to dst's H, W
             x = dst
         h1, w1 = s[1]
         out = torch.empty((n, self.cout, 2 * h1, 2 * w1), dtype=torch.float32, device=dev)
@@ -476,11 +489,12 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                 a = conv.forward(x, oh, ow, act=ACT_LEAKY, x_bordered=inp_b if i == 0 else None)
                 ws["a"][i] = a
             else:
-                y = conv.forward(x, oh, ow)
-                a = torch.empty_like(y)
                 sc = arena.take(conv.cout)
+                fuse = training and conv.stats_fusable()
+                y = conv.forward(x, oh, ow, bn_acc=sc["acc"] if fuse else None)
+                a = torch.empty_like(y)
                 ws["y"][i], ws["a"][i], ws["bn"][i] = y, a, sc
-                bn.forward(y, sc, training, a, ACT_LEAKY)
+                bn.forward(y, sc, training, a, ACT_LEAKY, stats_done=fuse)
             x = a
 
     def backward(self, ws, dout, need_input_grad, param_grads=True):

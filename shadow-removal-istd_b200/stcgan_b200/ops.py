@@ -65,9 +65,11 @@ def tc_eligible_wgrad(d0: int, d1: int) -> bool:
     return d0 % 128 == 0 and d1 % 64 == 0
 
 
-def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out_nchw=None, backend=BACKEND_FFMA):
+def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out_nchw=None, backend=BACKEND_FFMA,
+            bn_acc=None):
     """out[N,OH,OW,nout] = tap-GEMM(x, wp).  `out` may be a channel-slice view; `out_nchw` (fp32 [N,nout,OH,OW])
-    selects the NCHW epilogue instead."""
+    selects the NCHW epilogue instead.  `bn_acc` (fp64 [BN_SLOTS, 2, nout], zeroed by the caller; tensor-core backend
+    only): the following BatchNorm's batch statistics are accumulated by the GEMM epilogue."""
     _need_cuda(x, wp)
     n, ih, iw, k, ldx = _nhwc(x)
     lib = _lib.load()
@@ -83,6 +85,12 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
     if backend == BACKEND_TC and n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
         wst = torch.empty(n * oh * ow * nout, dtype=torch.float32, device=x.device)     # split-K partial sums
         ws, ws_bytes = wst.data_ptr(), wst.numel() * 4
+    if bn_acc is not None:
+        assert backend == BACKEND_TC and bias is None and act == ACT_NONE and not nchw
+        assert bn_acc.dtype == torch.float64 and bn_acc.is_contiguous() and bn_acc.numel() == _lib.BN_SLOTS * 2 * nout
+        check(lib.stcgan_tapconv_bnstats(geom, x.data_ptr(), n, ih, iw, k, ldx, wp.data_ptr(), y.data_ptr(), oh, ow, nout,
+                                         ldy, ws, ws_bytes, bn_acc.data_ptr(), _stream()), "stcgan_tapconv_bnstats")
+        return y
     check(lib.stcgan_tapconv(geom, _code(x), backend, x.data_ptr(), n, ih, iw, k, ldx, wp.data_ptr(),
                              None if bias is None else bias.data_ptr(), act, y.data_ptr(), oh, ow, nout, ldy, nchw,
                              ws, ws_bytes, _stream()), "stcgan_tapconv")
@@ -144,6 +152,23 @@ def bn_act_apply(y, scale_shift, out1, act1, out2=None, act2=ACT_NONE):
                                           None if scale_shift is None else scale_shift.data_ptr(), hc, wc,
                                           out1.data_ptr(), ld1, act1, None if out2 is None else out2.data_ptr(), ld2, act2,
                                           _stream()), "stcgan_bn_act_apply")
+
+
+def bn_fused_apply(y, acc, count, gamma, beta, rmean, rvar, momentum, eps, training, mean_invstd, scale_shift,
+                   out1, act1, out2=None, act2=ACT_NONE):
+    """bn_finalize + bn_act_apply in one launch; `acc` is fp64 [BN_SLOTS, 2, C] (training) or None (eval)."""
+    n, h, w, c, ldy = _nhwc(y)
+    n1, hc, wc, c1, ld1 = _nhwc(out1)
+    assert c1 == c and n1 == n
+    ld2 = 0
+    if out2 is not None:
+        _, h2, w2, c2, ld2 = _nhwc(out2)
+        assert (h2, w2, c2) == (hc, wc, c)
+    p = lambda t: None if t is None else t.data_ptr()
+    check(_lib.load().stcgan_bn_fused_apply(_code(y), y.data_ptr(), n, h, w, c, ldy, p(acc), count, gamma.data_ptr(),
+                                            beta.data_ptr(), p(rmean), p(rvar), momentum, eps, int(training),
+                                            mean_invstd.data_ptr(), scale_shift.data_ptr(), hc, wc, out1.data_ptr(), ld1,
+                                            act1, p(out2), ld2, act2, _stream()), "stcgan_bn_fused_apply")
 
 
 def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2, acc, dy, dgamma, dbeta):

@@ -125,6 +125,64 @@ def test_conv_reads_padding_out_of_range_and_writes_channel_slices(cuda, lib, mo
     assert float(buf[..., :64].abs().max()) == 0 and float(buf[..., 128:].abs().max()) == 0
 
 
+BNSTAT_CASES = [
+    ("conv2", 64, 128, 4, 32, 32),     # BN=128 tiles, several tiles per channel
+    ("conv2", 128, 64, 3, 16, 24),     # BN=64 tiles
+    ("conv2", 64, 64, 2, 15, 5),       # ragged tiles + out-of-range rows (must not count)
+    ("conv1", 256, 512, 2, 8, 8),      # stride 1, 7x7 out
+    ("convT", 128, 64, 2, 16, 16),     # four parity classes accumulate into the same channels
+    ("convT", 64, 128, 1, 5, 7),       # odd grid
+    ("convT", 1024, 512, 2, 2, 2),     # split-K path: statistics from the finisher kernel
+    ("conv2", 512, 512, 4, 4, 4),      # split-K path, Conv2d
+]
+
+
+@pytest.mark.parametrize("case", BNSTAT_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_epilogue_batchnorm_statistics(cuda, lib, case):
+    """BatchNorm batch statistics fused into the GEMM epilogue (stcgan_tapconv_bnstats) == sums over the bf16 conv output
+    the same launch wrote; then finalize+apply in one launch (stcgan_bn_fused_apply) against nn.BatchNorm2d semantics."""
+    from stcgan_b200 import _lib, ops
+    from stcgan_b200._lib import ACT_LEAKY, ACT_RELU
+    kind, cin, cout, n, h, w_ = case
+    op, w, _ = _convop(kind, cin, cout, "bf16", cuda)
+    assert op.stats_fusable()
+    g = torch.Generator().manual_seed(5)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), "bf16")
+    ph, pw = (h + h % 2, w_ + w_ % 2) if kind == "conv2" else (h, w_)
+    oh, ow = op.out_size(ph, pw)
+    acc = torch.zeros((_lib.BN_SLOTS, 2, cout), dtype=torch.float64, device=cuda)
+    y = op.forward(_nhwc(x, torch.bfloat16, cuda), oh, ow, bn_acc=acc)
+    y_plain = op.forward(_nhwc(x, torch.bfloat16, cuda), oh, ow)
+    torch.cuda.synchronize()
+    # (split-K layers reduce their partial sums with fp32 atomics in arbitrary order: equal up to a bf16 ulp only)
+    assert rel_err(y.float(), y_plain.float().cpu().double()) < 3e-3, "the statistics epilogue must not change the conv output"
+    yd = y.double().cpu().reshape(-1, cout)
+    tot = acc.sum(dim=0).cpu()
+    cnt = yd.shape[0]
+    assert rel_err(tot[0], yd.sum(0)) < 1e-5 and rel_err(tot[1], (yd * yd).sum(0)) < 1e-5
+    # finalize + apply, training mode, against torch on the same bf16 tensor
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    rm, rv = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+    mi = torch.empty((2, cout), device=cuda); ss = torch.empty((2, cout), device=cuda)
+    o1, o2 = torch.empty_like(y), torch.empty_like(y)
+    ops.bn_fused_apply(y, acc, cnt, gamma, beta, rm, rv, 0.1, 1e-5, True, mi, ss, o1, ACT_LEAKY, o2, ACT_RELU)
+    torch.cuda.synchronize()
+    bn = torch.nn.BatchNorm2d(cout).double()
+    with torch.no_grad():
+        bn.weight.copy_(gamma.double().cpu()); bn.bias.copy_(beta.double().cpu())
+    z = bn(_nchw(y).double())
+    assert rel_err(_nchw(o1), F.leaky_relu(z, 0.2)) < 6e-3 and rel_err(_nchw(o2), F.relu(z)) < 6e-3
+    assert rel_err(rm, bn.running_mean) < 1e-5 and rel_err(rv, bn.running_var) < 1e-5
+    assert rel_err(mi[0], yd.mean(0)) < 1e-5 and rel_err(mi[1], 1.0 / torch.sqrt(yd.var(0, unbiased=False) + 1e-5)) < 1e-5
+    # eval mode: running statistics, no accumulator
+    o3 = torch.empty_like(y)
+    ops.bn_fused_apply(y, None, cnt, gamma, beta, rm, rv, 0.0, 1e-5, False, mi, ss, o3, ACT_RELU)
+    torch.cuda.synchronize()
+    bn.eval()
+    assert rel_err(_nchw(o3), F.relu(bn(_nchw(y).double()))) < 6e-3
+
+
 def test_pack_weight_layout(cuda, lib):
     from stcgan_b200 import ops
     w = torch.randn(24, 40, 4, 4)

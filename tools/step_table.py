@@ -61,6 +61,10 @@ def describe(name, a, k):
         out2 = a[4] if len(a) > 4 else k.get("out2")
         by = yy.numel() * 2 + out1.numel() * 2 + (0 if out2 is None else out2.numel() * 2)
         return f"y{list(yy.shape)} ss={'y' if ss is not None else 'n'} out2={'y' if out2 is not None else 'n'}", 0, by
+    if name == "bn_fused_apply":
+        yy = a[0]; out1 = a[12]; out2 = a[14] if len(a) > 14 else k.get("out2")
+        by = yy.numel() * 2 + out1.numel() * 2 + (0 if out2 is None else out2.numel() * 2)
+        return f"y{list(yy.shape)} out2={'y' if out2 is not None else 'n'}", 0, by
     if name == "bn_act_bwd":
         yy, ss, mi, gamma, training, g1, act1, g2, act2, acc, dy = a[:11]
         e = dy.numel() * 2
@@ -87,7 +91,7 @@ def describe(name, a, k):
     return "", 0, 0
 
 
-names = ["tapconv", "tapconv_thin_n", "tapwgrad", "thinconv", "thinwgrad", "bn_stats", "bn_finalize", "bn_act_apply",
+names = ["tapconv", "tapconv_thin_n", "tapwgrad", "thinconv", "thinwgrad", "bn_stats", "bn_finalize", "bn_act_apply", "bn_fused_apply",
          "bn_act_bwd", "pack_input", "out_act_bwd", "unpack_input_grad", "colsum", "fused_loss", "pack_weight",
          "pack_weight_thin", "pack_weight_pad16"]
 rec, saved = [], {}
