@@ -140,6 +140,19 @@ int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void
  * wtap = flip ? 15 - tap : tap; t zero-bordered [N, HP, WP, 8] with thin_c real channels, f [N, FH, FW, Dfat] pitch ldf */
 int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_c, const void* f, int FH, int FW, int Dfat,
                      int ldf, int fat_is_dim0, int flip, float* G, void* stream);
+/* Thin-N convolutions as one pixel GEMM + in-CTA col2im (thin_col2im.cu): the fat input x [N, IH, IW, K] (pitch ldx) is read
+ * ONCE; Pm[pixel][(tap,c)] = x[pixel,:] . wt[(tap,c),:] on tcgen05 (N dimension = 16 taps x cpad channels), and the 16 tap
+ * planes are summed inside the CTA over overlapping pixel tiles, so every output is produced by exactly one CTA (no atomics).
+ *   mode 0: stride-2 scatter = nn.ConvTranspose2d(k4,s2,p1) forward (stcgan_g.py:93-95) and the input gradient of
+ *           nn.Conv2d(k4,s2,p1) (first layers, stcgan_g.py:85-86 outermost, stcgan_d.py:22-23);  OH <= 2*IH+1, OW <= 2*IW+1
+ *   mode 1: stride-1 gather = nn.Conv2d(k4,s1,p1) forward (stcgan_d.py:49-50);  OH = IH - 1, OW = IW - 1
+ * wt: [16*cpad][K] bf16 from stcgan_pack_weight_tapn, cpad in {1,4,8}, cout <= cpad real channels.
+ * Output: y_nchw_f32 [N, cout, OH, OW] with bias + activation (any STCGAN_ACT_*), or (mode 0 only, no bias / activation)
+ * y_nhwc8: bf16 [N, OH, OW, >= 8] pitch ldy, channels cout..7 written as zeros.  Exactly one of the two is non-NULL. */
+int stcgan_thin_col2im(int mode, const void* x, int N, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
+                       const float* bias, int act, float* y_nchw_f32, void* y_nhwc8, int ldy, int OH, int OW, void* stream);
+/* wt[(t*cpad + r)][k] = W(r, k, t) with (r, k) = (d0, d1) if n_is_d0 else (d1, d0), zero rows for r >= the thin dimension */
+int stcgan_pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, void* stream);
 /* thin weight packings from the torch parameter W[d0][d1][4][4] (fp32) to bf16 */
 int stcgan_pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, void* stream);
 int stcgan_pack_weight_pad16(const float* w, int D0, int D1, int n_is_d0, void* out, void* stream);

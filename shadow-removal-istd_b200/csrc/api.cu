@@ -26,6 +26,10 @@ int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const 
                  int fat_is_dim0, int flip, float* G, cudaStream_t st);
 int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
                 const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
+// thin_col2im.cu
+int thin_col2im_tc(int mode, const void* x, int NB, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
+                   const float* bias, int act, float* y32, void* y8, int ldy, int OH, int OW, cudaStream_t st);
+int pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, cudaStream_t st);
 // bn_act.cu
 int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st);
 int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
@@ -219,6 +223,20 @@ int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_
   STCGAN_REQUIRE(t && f && G && N >= 0 && HP >= 4 && WP >= 4 && (stride == 1 || stride == 2) && FH > 0 && FW > 0 && ldf >= Dfat);
   if (N == 0) return 0;
   return thinwgrad_tc(t, N, HP, WP, stride, thin_c, f, FH, FW, Dfat, ldf, fat_is_dim0, flip, G, as_stream(stream));
+}
+
+int stcgan_thin_col2im(int mode, const void* x, int N, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
+                       const float* bias, int act, float* y_nchw_f32, void* y_nhwc8, int ldy, int OH, int OW, void* stream) {
+  STCGAN_REQUIRE(x && wt && N >= 0 && IH > 0 && IW > 0 && K > 0 && ldx >= K && OH > 0 && OW > 0);
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_SIGMOID);
+  STCGAN_REQUIRE(mode == 0 ? (OH <= 2 * IH + 1 && OW <= 2 * IW + 1) : (mode == 1 && OH == IH - 1 && OW == IW - 1));
+  if (N == 0) return 0;
+  return thin_col2im_tc(mode, x, N, IH, IW, K, ldx, wt, cpad, cout, bias, act, y_nchw_f32, y_nhwc8, ldy, OH, OW, as_stream(stream));
+}
+
+int stcgan_pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, void* stream) {
+  STCGAN_REQUIRE(w && out && D0 > 0 && D1 > 0);
+  return pack_weight_tapn(w, D0, D1, n_is_d0, cpad, out, as_stream(stream));
 }
 
 int stcgan_pack_weight_thin(const float* w, int D0, int D1, int n_is_d0, int flip, void* out, void* stream) {

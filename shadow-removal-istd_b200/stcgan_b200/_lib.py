@@ -64,6 +64,8 @@ SIGNATURES = {
     "stcgan_tapconv_thin_n": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
     "stcgan_thinconv": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "stcgan_thinwgrad": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "stcgan_thin_col2im": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "stcgan_pack_weight_tapn": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight_thin": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight_pad16": (_i, [_p, _i, _i, _i, _p, _p]),
     "stcgan_unpack_input_grad": (_i, [_i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),

@@ -41,7 +41,8 @@ class ConvOp:
         # "coutT" = ConvTranspose2d with <= 8 output channels (G's last layer), "cout1" = stride-1 Conv2d with <= 8
         # output channels (D's last layer).  See include/stcgan_b200.h "thin layers".
         self.thin = None
-        self.wthin = self.wp16 = None
+        self.wthin = self.wtn = None
+        self.cpad = 0
 
     # ---- packing ------------------------------------------------------------------------
     def ensure_packed(self, act_dtype, force=False):
@@ -63,17 +64,20 @@ class ConvOp:
                     self.thin = "cout1"
             if self.thin is not None:
                 fat = self.cout if self.thin == "cin" else self.cin
+                nthin = self.cin if self.thin == "cin" else self.cout
+                self.cpad = 1 if nthin == 1 else (4 if nthin <= 4 else 8)
                 if self.wthin is None or self.wthin.device != w.device:
                     self.wthin = torch.empty((fat, 128), dtype=torch.bfloat16, device=w.device)
-                    self.wp16 = torch.empty((16, 16, fat), dtype=torch.bfloat16, device=w.device)
-                if self.thin == "cin":        # fwd: thin K over ci;  dgrad: thin N over ci
+                    self.wtn = torch.empty((16 * self.cpad, fat), dtype=torch.bfloat16, device=w.device)
+                # wthin: thin-K operand [fat][(tap, c)];  wtn: thin-N operand [(tap, c)][fat] of the pixel GEMM + col2im path
+                if self.thin == "cin":        # fwd: thin K over ci;  dgrad: thin N over ci (= d1)
                     ops.pack_weight_thin(wc, True, False, self.wthin)
-                    ops.pack_weight_pad16(wc, False, self.wp16)
+                    ops.pack_weight_tapn(wc, False, self.cpad, self.wtn)
                 elif self.thin == "coutT":    # fwd: thin N over co (= d1);  dgrad: thin K over co, rows ci (= d0)
-                    ops.pack_weight_pad16(wc, False, self.wp16)
+                    ops.pack_weight_tapn(wc, False, self.cpad, self.wtn)
                     ops.pack_weight_thin(wc, True, False, self.wthin)
                 else:                         # fwd: thin N over co (= d0);  dgrad: thin K over co with flipped taps
-                    ops.pack_weight_pad16(wc, True, self.wp16)
+                    ops.pack_weight_tapn(wc, True, self.cpad, self.wtn)
                     ops.pack_weight_thin(wc, False, True, self.wthin)
             self.version = ver
         self.use_tc = act_dtype == torch.bfloat16
@@ -106,7 +110,8 @@ class ConvOp:
         if self.thin == "cin" and x_bordered is not None and out_nchw is None:
             return ops.thinconv(x_bordered, 2, self.wthin, self.cout, oh, ow, bias=bias, act=act, out=out)
         if self.thin in ("coutT", "cout1") and out_nchw is not None:
-            ops.tapconv_thin_n(geom, x, self.wp16, self.cout, oh, ow, bias=bias, act=act, out_nchw=out_nchw)
+            ops.thin_col2im(0 if self.thin == "coutT" else 1, x, self.wtn, self.cpad, self.cout, oh, ow, bias=bias, act=act,
+                            out_nchw=out_nchw)
             return out_nchw
         plain = out_nchw is None and act in (ACT_NONE, ACT_LEAKY, ACT_RELU)
         return ops.tapconv(geom, x, wp, self.cout, oh, ow, bias=bias, act=act, out=out, out_nchw=out_nchw,
@@ -119,7 +124,7 @@ class ConvOp:
         geom = {"conv2": GEOM_PARITY, "conv1": GEOM_WIN_S1_FLIP, "convT": GEOM_WIN_S2}[self.kind]
         wp = self.p1 if self.kind == "convT" else self.p2
         if self.thin == "cin" and out8 is not None:
-            ops.tapconv_thin_n(geom, g, self.wp16, self.cin, ih, iw, out8=out8)
+            ops.thin_col2im(0, g, self.wtn, self.cpad, self.cin, ih, iw, out8=out8)
             return out8
         if self.thin in ("coutT", "cout1") and g_bordered is not None:
             return ops.thinconv(g_bordered, 2 if self.thin == "coutT" else 1, self.wthin, self.cin, ih, iw, out=out)

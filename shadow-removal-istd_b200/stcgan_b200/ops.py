@@ -233,6 +233,30 @@ def tapconv_thin_n(geom, x, wp16, nout, oh, ow, *, bias=None, act=ACT_NONE, out8
           "stcgan_tapconv_thin_n")
 
 
+def thin_col2im(mode, x, wt, cpad, cout, oh, ow, *, bias=None, act=ACT_NONE, out_nchw=None, out8=None):
+    """thin-N convolution as one pixel GEMM + in-CTA col2im (x is read once): mode 0 = ConvTranspose2d forward / Conv2d-s2
+    input gradient, mode 1 = Conv2d(k4,s1,p1) forward.  Output NCHW fp32 (bias + activation) or 8-channel NHWC bf16."""
+    _need_cuda(x, wt)
+    n, ih, iw, k, ldx = _nhwc(x)
+    assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and wt.numel() == 16 * cpad * k
+    ldy = 0
+    if out8 is not None:
+        _, _, _, _, ldy = _nhwc(out8)
+    else:
+        assert out_nchw.dtype == torch.float32 and out_nchw.is_contiguous() and tuple(out_nchw.shape) == (n, cout, oh, ow)
+    check(_lib.load().stcgan_thin_col2im(mode, x.data_ptr(), n, ih, iw, k, ldx, wt.data_ptr(), cpad, cout,
+                                         None if bias is None else bias.data_ptr(), act,
+                                         None if out_nchw is None else out_nchw.data_ptr(),
+                                         None if out8 is None else out8.data_ptr(), ldy, oh, ow, _stream()),
+          "stcgan_thin_col2im")
+
+
+def pack_weight_tapn(w, n_is_d0, cpad, out):
+    d0, d1 = w.shape[0], w.shape[1]
+    check(_lib.load().stcgan_pack_weight_tapn(w.data_ptr(), d0, d1, int(n_is_d0), cpad, out.data_ptr(), _stream()),
+          "stcgan_pack_weight_tapn")
+
+
 def thinconv(t, stride, wthin, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None):
     """thin-K convolution of a zero-bordered 8-channel tensor t [N, HP, WP, 8] (tensor cores)."""
     n, hp, wp_, c, _ = _nhwc(t)

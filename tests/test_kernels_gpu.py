@@ -347,13 +347,20 @@ THIN_CASES = [
     ("convT", 128, 3, 3, 8, 12),      # G2 d1
     ("conv1", 512, 1, 2, 9, 9),       # D c5 (+bias)
     ("conv1", 512, 1, 3, 31, 31),     # D c5 at the 256x256 geometry
+    ("conv2", 7, 64, 1, 37, 53),      # odd sizes: the input gradient's last row / column come from one tap only
+    ("conv2", 4, 64, 2, 64, 96),      # many overlapping col2im tiles
+    ("convT", 64, 3, 1, 40, 50),      # col2im tiles that do not divide the image
+    ("convT", 128, 1, 1, 3, 5),       # image smaller than one tile
+    ("conv1", 64, 1, 2, 20, 45),      # stride-1 gather over several tiles
+    ("conv1", 128, 3, 1, 6, 7),       # three output channels through the stride-1 gather
 ]
 
 
 @pytest.mark.parametrize("case", THIN_CASES, ids=lambda c: "-".join(map(str, c)))
 def test_thin_layers_on_tensor_cores(cuda, lib, case):
-    """thin-K (5-D im2col TMA view of a zero-bordered 8-channel tensor), thin-N (N padded to 16 in the weights only)
-    and thin wgrad kernels against the torch ops they replace, bf16 inputs, identical data."""
+    """thin-K (5-D im2col TMA view of a zero-bordered 8-channel tensor), thin-N (pixel GEMM with the taps in the N
+    dimension + in-CTA col2im, stcgan_thin_col2im) and thin wgrad kernels against the torch ops they replace, bf16 inputs,
+    identical data."""
     from stcgan_b200 import ops
     from stcgan_b200._lib import ACT_NONE, ACT_TANH
     kind, cin, cout, n, h, w_ = case
