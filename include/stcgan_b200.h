@@ -191,19 +191,22 @@ int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, 
                           float* mean_invstd, float* scale_shift, int HC, int WC,
                           void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
 /* backward, pass 1: dz = g1*act1'(z) + g2*act2'(z) (z = y*scale+shift, zero outside the crop);
- * acc[0][c] += sum dz, acc[1][c] += sum dz*xhat   (fp64, caller zeroes) */
+ * acc[slot][0][c] += sum dz, acc[slot][1][c] += sum dz*(y-mean)   (fp64; acc is [STCGAN_BN_SLOTS][2][C], caller zeroes;
+ * the blocks spread their atomics over the slots) */
 int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy,
                              const float* scale_shift, const float* mean_invstd, int HC, int WC,
                              const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
                              double* acc, void* stream);
-/* backward, pass 2: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))  (training)
- *                   dy = gamma*invstd*dz (eval) ;  dy = dz (scale_shift == NULL: no BatchNorm)
- * also dgamma += acc[1], dbeta += acc[0] (by the first block; NULL = skip). */
+/* backward, pass 2: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))  (training; the means come from the sum of
+ *                   the slots of acc);  dy = gamma*invstd*dz (eval) ;  dy = dz (scale_shift == NULL: no BatchNorm)
+ * also dgamma += invstd*sum(acc[.][1]), dbeta += sum(acc[.][0]) (by the first block; NULL = skip), and, if dbias != NULL,
+ * dbias[c] += sum_p dy[p,c] (the bias gradient of a preceding biased conv: stcgan_d.py:22-23). */
 int stcgan_bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
                             const float* scale_shift, const float* mean_invstd, const float* gamma,
                             int training, int HC, int WC,
                             const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
-                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, void* stream);
+                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, float* dbias,
+                            void* stream);
 /* column sums of g [P x C] (pitch ld) added to fp32 out[C]  (bias gradients, stcgan_g.py:93-95, stcgan_d.py:22-23,49-50) */
 int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out, void* stream);
 

@@ -42,7 +42,7 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
 int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
                      const float* gamma, int training, int HC, int WC, const void* g1, int ldg1, int act1,
                      const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
-                     float* dgamma, float* dbeta, cudaStream_t st);
+                     float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
 int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cudaStream_t st);
 int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const double* acc, long long count,
                    const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps, int training,
@@ -183,10 +183,11 @@ int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int 
 int stcgan_bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
                             const float* mean_invstd, const float* gamma, int training, int HC, int WC,
                             const void* g1, int ldg1, int act1, const void* g2, int ldg2, int act2,
-                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, void* stream) {
+                            const double* acc, void* dy, int lddy, float* dgamma, float* dbeta, float* dbias,
+                            void* stream) {
   STCGAN_REQUIRE(dtype_ok(dtype) && y && HC <= H && WC <= W);
   return bn_act_bwd_apply(dtype, y, N, H, W, C, ldy, scale_shift, mean_invstd, gamma, training, HC, WC, g1, ldg1, act1,
-                          g2, ldg2, act2, acc, dy, lddy, dgamma, dbeta, as_stream(stream));
+                          g2, ldg2, act2, acc, dy, lddy, dgamma, dbeta, dbias, as_stream(stream));
 }
 
 int stcgan_colsum(int dtype, const void* g, int64_t P, int C, int ld, float* out, void* stream) {

@@ -372,30 +372,32 @@ struct BwdIn {
   }
 };
 
-// pass 1: acc[0][c] += sum dz ; acc[1][c] += sum dz * (y - mean)        (fp64 across threads / blocks)
+// pass 1: acc[slot][0][c] += sum dz ; acc[slot][1][c] += sum dz * (y - mean)   (fp64 across threads / blocks; the blocks
+// spread their atomics over STCGAN_BN_SLOTS partial slots, pass 2 adds the slots up)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
                      const float* __restrict__ ss, const float* __restrict__ mi, int HC, int WC,
                      const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
                      double* __restrict__ acc, int cv, int rows) {
-  pdl_prologue();
   extern __shared__ float red[];
+  pdl_prologue();
   const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool active = tr < rows;
   const bool two = g2 != nullptr;
+  double* acc_slot = acc + (long long)(blockIdx.x % STCGAN_BN_SLOTS) * 2 * C;
   for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
     float sc[8], sh[8], mean[8], s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; s[i] = 0.f; q[i] = 0.f; }
     if (active) {
       const long long stride = (long long)gridDim.x * rows;
-      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
-        BwdIn<T> in[2];
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
+        BwdIn<T> in[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+        for (int u = 0; u < 4; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 4; ++u)
           if (p + u * stride < P) {
             float dz[8], yv[8];
             in[u].dz(sc, sh, act1, act2, two, dz, yv);
@@ -414,70 +416,93 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
       double ds = 0.0, dq = 0.0;
       for (int r = 0; r < rows; ++r) { ds += rs[r * cv * VEC + j]; dq += rq[r * cv * VEC + j]; }
       const int c = (c0 - tc * VEC) + j;
-      atomicAdd(&acc[c], ds);
-      atomicAdd(&acc[C + c], dq);
+      atomicAdd(&acc_slot[c], ds);
+      atomicAdd(&acc_slot[C + c], dq);
     }
     __syncthreads();
   }
 }
 
 // pass 2: dy = A*dz - B - (y - mean)*Cc  with A = gamma*invstd, B = A*mean(dz), Cc = A*invstd^2*mean(dz*(y-mean))
-//         (training);  dy = A*dz (eval);  dy = dz (no BatchNorm).  dgamma += invstd*acc[1], dbeta += acc[0].
+//         (training);  dy = A*dz (eval);  dy = dz (no BatchNorm).  dgamma += invstd*acc[1], dbeta += acc[0] (block 0).
+//         The per-channel coefficients are derived once per block into shared memory (sum over the statistic slots).
+//         dbias (optional, layers with a conv bias and no BatchNorm): dbias[c] += sum_p dy[p, c].
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
                     const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ gamma,
                     int training, int HC, int WC,
                     const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
                     const double* __restrict__ acc, T* __restrict__ dy, int lddy,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, int cv, int rows) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int cv, int rows) {
+  extern __shared__ float coef[];     // [5][C]: sc, sh, kA, kB, kC   (+ [rows][cv*8] bias-gradient scratch behind it)
   pdl_prologue();
-  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
   const bool has_bn = ss != nullptr;
   const bool two = g2 != nullptr;
-  if (has_bn && blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dgamma[c] += (float)(acc[C + c] * (double)mi[C + c]);
-      dbeta[c] += (float)acc[c];
-    }
-  }
-  if (tr >= rows) return;
   const double invP = 1.0 / (double)P;
-  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
-    float sc[8], sh[8], kA[8], kB[8], kC[8];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc = 1.f, sh = 0.f, kA = 1.f, kB = 0.f, kC = 0.f;
+    if (has_bn) {
+      sc = ss[c]; sh = ss[C + c];
+      const float mean = mi[c], invstd = mi[C + c];
+      kA = gamma[c] * invstd;
+      if (training) {
+        double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (has_bn) {
-        sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i];
-        const float mean = mi[c0 + i], invstd = mi[C + c0 + i];
-        const float A = gamma[c0 + i] * invstd;
-        kA[i] = A;
-        if (training) {
-          const float cc = A * invstd * invstd * (float)(acc[C + c0 + i] * invP);
-          kC[i] = cc;
-          kB[i] = A * (float)(acc[c0 + i] * invP) - mean * cc;      // folded: -(y - mean)*cc = -y*cc + mean*cc
-        } else {
-          kC[i] = 0.f; kB[i] = 0.f;
-        }
-      } else {
-        sc[i] = 1.f; sh[i] = 0.f; kA[i] = 1.f; kB[i] = 0.f; kC[i] = 0.f;
+        for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { a0 += acc[(2 * k) * C + c]; a1 += acc[(2 * k + 1) * C + c]; }
+        kC = kA * invstd * invstd * (float)(a1 * invP);
+        kB = kA * (float)(a0 * invP) - mean * kC;        // folded: -(y - mean)*kC = -y*kC + mean*kC
+        if (blockIdx.x == 0 && dgamma) { dgamma[c] += (float)(a1 * (double)invstd); dbeta[c] += (float)a0; }
+      } else if (blockIdx.x == 0 && dgamma && acc) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { a0 += acc[(2 * k) * C + c]; a1 += acc[(2 * k + 1) * C + c]; }
+        dgamma[c] += (float)(a1 * (double)invstd); dbeta[c] += (float)a0;
       }
     }
-    const long long stride = (long long)gridDim.x * rows;
-    for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 2 * stride) {
-      BwdIn<T> in[2];
+    coef[c] = sc; coef[C + c] = sh; coef[2 * C + c] = kA; coef[3 * C + c] = kB; coef[4 * C + c] = kC;
+  }
+  __syncthreads();
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  const bool active = tr < rows;
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8], kA[8], kB[8], kC[8], bs[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = coef[c0 + i]; sh[i] = coef[C + c0 + i]; kA[i] = coef[2 * C + c0 + i]; kB[i] = coef[3 * C + c0 + i];
+      kC[i] = coef[4 * C + c0 + i]; bs[i] = 0.f;
+    }
+    if (active) {
+      const long long stride = (long long)gridDim.x * rows;
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
+        BwdIn<T> in[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-        if (p + u * stride < P) {
-          float dz[8], yv[8];
-          in[u].dz(sc, sh, act1, act2, two, dz, yv);
-          Vec8<T> o;
+        for (int u = 0; u < 4; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - yv[i] * kC[i];
-          o.store(dy + (p + u * stride) * lddy + c0);
-        }
+        for (int u = 0; u < 4; ++u)
+          if (p + u * stride < P) {
+            float dz[8], yv[8];
+            in[u].dz(sc, sh, act1, act2, two, dz, yv);
+            Vec8<T> o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - yv[i] * kC[i]; bs[i] += o.v[i]; }
+            o.store(dy + (p + u * stride) * lddy + c0);
+          }
+      }
+    }
+    if (dbias) {      // block-level column sums, one fp32 atomic per channel and block
+      float* rb = coef + 5 * C;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rb[(tr * cv + tc) * VEC + i] = bs[i];
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < cv * VEC; j += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += rb[r * cv * VEC + j];
+        atomicAdd(&dbias[(c0 - tc * VEC) + j], t);
+      }
+      __syncthreads();
     }
   }
 }
@@ -588,10 +613,10 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
   const RowMap m = row_map(C);
   const size_t smem = (size_t)2 * m.rows * m.cv * VEC * sizeof(float);
   if (dtype == STCGAN_F32)
-    launch_k(bn_bwd_reduce_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 2), 256, smem, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
+    launch_k(bn_bwd_reduce_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 4), 256, smem, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
         static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
   else
-    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 2), 256, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
+    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 4), 256, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
         act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
   return finish_launch();
 }
@@ -599,7 +624,7 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
 int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
                      const float* gamma, int training, int HC, int WC, const void* g1, int ldg1, int act1,
                      const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
-                     float* dgamma, float* dbeta, cudaStream_t st) {
+                     float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
   if (C % VEC != 0 || C > 2048 || !g1 || !dy || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2) ||
       !vec_ok(dtype, dy, lddy))
     return STCGAN_EINVAL;
@@ -607,13 +632,16 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
   const long long P = (long long)N * H * W;
   if (P == 0) return 0;
   const RowMap m = row_map(C);
+  const size_t smem = (size_t)5 * C * sizeof(float) + (dbias ? (size_t)m.rows * m.cv * VEC * sizeof(float) : 0);
   if (dtype == STCGAN_F32)
-    launch_k(bn_bwd_apply_kernel<float>, stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<float>, 0), 256, 0, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
-        act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
+    launch_k(bn_bwd_apply_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<float>, smem), 256, smem, st,
+             static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
+             act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows);
   else
-    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 2, bn_bwd_apply_kernel<__nv_bfloat16>, 0), 256, 0, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
-        static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
-        static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, m.cv, m.rows);
+    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
+             static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
+             static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
+             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows);
   return finish_launch();
 }
 

@@ -58,7 +58,7 @@ SIGNATURES = {
     "stcgan_bn_act_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
     "stcgan_bn_act_bwd_reduce": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p]),
     "stcgan_bn_act_bwd_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _i, _i,
-                                     _p, _p, _i, _p, _p, _p]),
+                                     _p, _p, _i, _p, _p, _p, _p]),
     "stcgan_colsum": (_i, [_i, _p, _i64, _i, _i, _p, _p]),
     "stcgan_pack_input": (_i, [_i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_tapconv_thin_n": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),

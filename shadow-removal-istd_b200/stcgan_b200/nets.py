@@ -130,11 +130,12 @@ class ConvOp:
             return ops.thinconv(g_bordered, 2 if self.thin == "coutT" else 1, self.wthin, self.cin, ih, iw, out=out)
         return ops.tapconv(geom, g, wp, self.cin, ih, iw, out=out, backend=self._backend_conv(self.cout, self.cin))
 
-    def wgrad(self, x, g, *, x_bordered=None, g_bordered=None):
-        """accumulate the packed weight gradient from the layer input x and output gradient g."""
+    def wgrad(self, x, g, *, x_bordered=None, g_bordered=None, bias_done=False):
+        """accumulate the packed weight gradient from the layer input x and output gradient g (`bias_done`: the bias
+        gradient was already accumulated by the activation-backward pass that produced g)."""
         if self.thin == "cin" and x_bordered is not None:
             ops.thinwgrad(x_bordered, 2, self.cin, g, self.g, True, False)
-            if self.bias is not None and self.gb is not None:
+            if self.bias is not None and self.gb is not None and not bias_done:
                 ops.colsum(g, self.gb)
             return
         if self.thin in ("coutT", "cout1") and g_bordered is not None:
@@ -518,13 +519,17 @@ class DiscriminatorRuntime(_NetRuntimeBase):
             g = ops.out_act_bwd(oact, ws["out"], dout, dt)
         for i in range(nl - 1, -1, -1):
             conv = self.layers[i]
+            bias_done = False
             thin_in = i == 0 and ws["inp_b"] is not None
             x_in = ws["a"][i - 1] if i > 0 else (None if thin_in else ws["inp"][..., :self.cin])
             if i < nl - 1:
                 bn = self.layer_bns[i]
                 if bn is None:
                     gy = torch.empty_like(ws["a"][i])
-                    ops.bn_act_bwd(ws["a"][i], None, None, None, training, g, ACT_LEAKY, None, ACT_NONE, None, gy, None, None)
+                    fuse_bias = param_grads and thin_in and conv.bias is not None and conv.gb is not None
+                    ops.bn_act_bwd(ws["a"][i], None, None, None, training, g, ACT_LEAKY, None, ACT_NONE, None, gy, None, None,
+                                   dbias=conv.gb if fuse_bias else None)
+                    bias_done = fuse_bias
                 else:
                     gy = torch.empty_like(ws["y"][i])
                     bn.backward(ws["y"][i], ws["bn"][i], training, g, ACT_LEAKY, None, ACT_NONE, gy, param_grads, zero_acc=False)
@@ -536,7 +541,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                 g = conv.dgrad(None, *s[i], g_bordered=g_b)
                 continue
             if param_grads:
-                conv.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None)
+                conv.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None, bias_done=bias_done)
             if i > 0:
                 g = conv.dgrad(gy, *s[i])
             elif need_input_grad:

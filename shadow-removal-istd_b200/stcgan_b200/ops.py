@@ -171,8 +171,9 @@ def bn_fused_apply(y, acc, count, gamma, beta, rmean, rvar, momentum, eps, train
                                             act1, p(out2), ld2, act2, _stream()), "stcgan_bn_fused_apply")
 
 
-def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2, acc, dy, dgamma, dbeta):
-    """Two-pass BN(+activation) backward; with scale_shift None this is the plain activation backward."""
+def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2, acc, dy, dgamma, dbeta, dbias=None):
+    """Two-pass BN(+activation) backward; with scale_shift None this is the plain activation backward.  `acc`: fp64
+    [BN_SLOTS, 2, C], zeroed.  `dbias` (fp32 [C]): also accumulates the column sums of dy (bias gradient)."""
     n, h, w, c, ldy = _nhwc(y)
     _, hc, wc, _, ldg1 = _nhwc(g1)
     ldg2 = 0
@@ -193,7 +194,7 @@ def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2,
                                            acc.data_ptr(), _stream()), "stcgan_bn_act_bwd_reduce")
     check(lib.stcgan_bn_act_bwd_apply(_code(y), y.data_ptr(), n, h, w, c, ldy, p(scale_shift), p(mean_invstd), p(gamma),
                                       int(training), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2, p(acc),
-                                      dy.data_ptr(), lddy, p(dgamma), p(dbeta), _stream()), "stcgan_bn_act_bwd_apply")
+                                      dy.data_ptr(), lddy, p(dgamma), p(dbeta), p(dbias), _stream()), "stcgan_bn_act_bwd_apply")
 
 
 def colsum(g, out):
