@@ -54,6 +54,7 @@ struct alignas(64) TapGemmParams {
   // (fp32 over the 128 rows of a tile, then fp64 atomics) into bn_acc[slot][2][bn_c], slot = CTA index % STCGAN_BN_SLOTS
   double* bn_acc;
   int bn_c;
+  int dbg_mode;            // timing experiments only (STCGAN_TC_DBGMODE): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
 };
 
 __device__ __forceinline__ long long gtime() {
@@ -120,49 +121,80 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
 
   if (threadIdx.x == 0) {
     // ===== TMA producer =====
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const int j = tap0 + it / P.kchunks, kc = it % P.kchunks;
-      uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
-      uint8_t* b_dst = a_dst + SM::A_BYTES;
-      mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
-      if (P.thin_k) {
-        // one 64-byte line per (pixel, kernel row): TMA gives every inner line its own swizzle-span row, so the two
-        // kernel rows of this K chunk are two consecutive [128 px][64 B] SWIZZLE_64B blocks (kernel row = slowest box dim)
-        tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, b0, a0, n0, 2 * kc);   // both kernel rows in one instruction
-      } else
-        tma_load_4d(&P.amap[P.tview[cls][j]], &full_bar[s], a_dst, kc * TC_BK, b0 + P.tdx[cls][j], a0 + P.tdy[cls][j], n0);
-      tma_load_2d(&P.bmap, &full_bar[s], b_dst, kc * TC_BK, (int)P.twt[cls][j] * P.Nout + n_col0);
+    // One thread feeds the whole CTA, so its per-stage instruction chain IS the pipeline's upper rate: ring slot / phase
+    // are carried incrementally (no divisions) and the tap table entries of the next tap are fetched one tap ahead.
+    int s = 0; uint32_t ph = 0;
+    if (P.thin_k) {
+      for (int kc = 0; kc < iters; ++kc) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+        if (P.dbg_mode & 2) { mbar_arrive(&full_bar[s]); }
+        else {
+          mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+          // one 64-byte line per (pixel, kernel row): TMA gives every inner line its own swizzle-span row, so the two
+          // kernel rows of this K chunk are two consecutive [128 px][64 B] SWIZZLE_64B blocks (kernel row = slowest box dim)
+          tma_load_5d(&P.amap[0], &full_bar[s], a_dst, 0, b0, a0, n0, 2 * kc);   // both kernel rows in one instruction
+          tma_load_2d(&P.bmap, &full_bar[s], a_dst + SM::A_BYTES, kc * TC_BK, n_col0);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    } else {
+      const int kchunks = P.kchunks;
+      int view = P.tview[cls][tap0], cx = b0 + P.tdx[cls][tap0], cy = a0 + P.tdy[cls][tap0];
+      int wrow = (int)P.twt[cls][tap0] * P.Nout + n_col0;
+      for (int j = 0; j < taps_here; ++j) {
+        const CUtensorMap* am = &P.amap[view];
+        const int cxj = cx, cyj = cy, wrowj = wrow;
+        if (j + 1 < taps_here) {      // next tap's table entries, off the critical path
+          const int jn = tap0 + j + 1;
+          view = P.tview[cls][jn]; cx = b0 + P.tdx[cls][jn]; cy = a0 + P.tdy[cls][jn];
+          wrow = (int)P.twt[cls][jn] * P.Nout + n_col0;
+        }
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_dst = smem + s * SM::STAGE_BYTES;
+          if (P.dbg_mode & 2) { mbar_arrive(&full_bar[s]); }
+          else {
+            mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
+            tma_load_4d(am, &full_bar[s], a_dst, kc * TC_BK, cxj, cyj, n0);
+            tma_load_2d(&P.bmap, &full_bar[s], a_dst + SM::A_BYTES, kc * TC_BK, wrowj);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
     }
   } else if (threadIdx.x == 32) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
+    int s = 0; uint32_t ph = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const bool thin_k = P.thin_k != 0, no_mma = (P.dbg_mode & 1) != 0;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(&full_bar[s], ph);
       if (it == 0) DBG_T(2);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+      const uint32_t a_addr = smem_base + s * SM::STAGE_BYTES;
       const uint32_t b_addr = a_addr + SM::A_BYTES;
-      if (P.thin_k) {
+      if (no_mma) { mbar_arrive(&empty_bar[s]); }
+      else {
+        if (thin_k) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // block k/2 (kernel row), 16 K-elements k%2 inside its 64-byte rows
-          const uint64_t ad = make_smem_desc(a_addr + (k >> 1) * 8192 + (k & 1) * 32, 16, 512, 4);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
-        }
-      } else {
+          for (int k = 0; k < 4; ++k) {   // block k/2 (kernel row), 16 K-elements k%2 inside its 64-byte rows
+            const uint64_t ad = make_smem_desc(a_addr + (k >> 1) * 8192 + (k & 1) * 32, 16, 512, 4);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
+        } else {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
         }
+        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
       }
-      umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     umma_commit(tmem_full);
     DBG_T(3);
@@ -175,7 +207,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     const int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
     const bool valid = n < P.N && oy < P.OH && ox < P.OW;
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
-    mbar_wait(tmem_full, 0);
+    mbar_wait_warp(tmem_full, 0, lane);
     if (threadIdx.x == 64) DBG_T(4);
     tc_fence_after();
     if constexpr (BN == 16) {
@@ -329,9 +361,6 @@ struct PersistSmem {
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
@@ -444,7 +473,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
       const bool valid = n < P.N && oy < P.OH && ox < P.OW;
       __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
       const uint32_t buf = li & 1u;
-      mbar_wait(&tmem_full[buf], (li >> 1) & 1u);
+      mbar_wait_warp(&tmem_full[buf], (li >> 1) & 1u, lane);
       tc_fence_after();
       __syncwarp();                                   // previous tile's row stores of this warp have read the staging rows
 #pragma unroll 1
@@ -645,7 +674,7 @@ tapgemm_tc_pair_kernel(const __grid_constant__ TapGemmParams P) {
     const int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
     const bool valid = n < P.N && oy < P.OH && ox < P.OW;
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
-    mbar_wait(tmem_full, 0);
+    mbar_wait_warp(tmem_full, 0, lane);
     if (threadIdx.x == 64) DBG_T(4);
     tc_fence_after();
     const uint32_t stg = smem_u32(smem) + (uint32_t)row * SM::PITCH;
@@ -803,7 +832,7 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
   } else if (warp >= 2) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    mbar_wait(tmem_full, 0);
+    mbar_wait_warp(tmem_full, 0, lane);
     tc_fence_after();
     if (P.thin) {
       const int wtap = P.flip ? 15 - row / 8 : row / 8, c = row % 8;
@@ -1050,6 +1079,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   memset(&P, 0, sizeof(P));
   P.nout_real = Nout; P.y32 = y32;
   P.bn_acc = bn_acc; P.bn_c = Nout;
+  { const char* e = getenv("STCGAN_TC_DBGMODE"); P.dbg_mode = e ? atoi(e) : 0; }
   const int n_rows = thin_n ? 16 : Nout;     // rows per tap in the packed weight matrix
   int GH = 0, GW = 0;
   for (int c = 0; c < g.nclass; ++c) {
@@ -1157,8 +1187,24 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   // against 0.21 us with two resident CTAs)
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   const bool deep = ctas <= 148 && g.ntaps * P.kchunks >= 8 && deep_ring_mode();
-  if (BN == 128) return deep ? launch_tapgemm<128, 6>(P, grid, st) : launch_tapgemm<128, 3>(P, grid, st);
-  return deep ? launch_tapgemm<64, 8>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
+  // STCGAN_TC_STAGES=n (experiments): force the ring depth (fewer stages = more resident CTAs per SM)
+  int force = 0;
+  { const char* e = getenv("STCGAN_TC_STAGES"); if (e) force = atoi(e); }
+  if (BN == 128) {
+    if (force == 2) return launch_tapgemm<128, 2>(P, grid, st);
+    if (force == 3) return launch_tapgemm<128, 3>(P, grid, st);
+    return deep ? launch_tapgemm<128, 6>(P, grid, st) : launch_tapgemm<128, 3>(P, grid, st);
+  }
+  if (force == 2) return launch_tapgemm<64, 2>(P, grid, st);
+  if (force == 3) return launch_tapgemm<64, 3>(P, grid, st);
+  if (force == 4) return launch_tapgemm<64, 4>(P, grid, st);
+  if (deep) return launch_tapgemm<64, 8>(P, grid, st);
+  // 128x64 tiles are cheap (half a 128x128 step per stage) and their launches have thousands of CTAs with short K loops:
+  // the per-CTA fixed cost (prologue, first TMA round trip, epilogue) is hidden by residency, not by ring depth --
+  // measured on B200 (tools/conv_probe.py): 2048 CTAs x 8 steps 47.7 us with 4 stages / 2 CTAs per SM, 38.5 us with
+  // 3 stages / 3 CTAs, 35.3 us with 2 stages / 4 CTAs; 2048 CTAs x 16 steps 68.0 -> 55.4 -> 55.2 us
+  if (g.ntaps * P.kchunks <= 8) return launch_tapgemm<64, 2>(P, grid, st);
+  return launch_tapgemm<64, 3>(P, grid, st);
 }
 
 // 5D im2col view of a zero-bordered 8-channel tensor T [N, HP, WP, 8]:

@@ -14,6 +14,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -32,6 +35,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin == 1024) t0 = clock64();
     if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
+}
+// Whole-warp wait with ONE polling lane: the accumulator-ready wait of the epilogue warps lasts for the entire main loop, and
+// every poll is a shared-memory access that competes with the tensor core's operand reads (a 128x128x16 MMA streams
+// ~124 B/clk out of the 128 B/clk the SM's shared memory delivers): 128 spinning threads measurably slow the MMAs down.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = clock64();
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");     // suspend-time hint: 10 ms (wakes on completion)
+      if (done) break;
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -119,7 +119,7 @@ pixgemm_col2im_kernel(const __grid_constant__ PixGemmParams P) {
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // accumulator row = input pixel (lh * tw + lw) of the tile
     float* Ps = reinterpret_cast<float*>(smem);    // [128][P_PITCH], aliases the (drained) pipeline ring
-    mbar_wait(tmem_full, 0);
+    mbar_wait_warp(tmem_full, 0, lane);
     tc_fence_after();
     if constexpr (NN == 16) {
       uint32_t r[16];

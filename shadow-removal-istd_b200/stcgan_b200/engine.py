@@ -81,6 +81,11 @@ class STCGANEngine:
             rt.ensure_packed()
             rt.alloc_grads()
         self.device = self.rt["G1"].device()
+        # weight-gradient kernels run on a side stream, concurrently with the dgrad / BatchNorm chain (nets._wgrad_async)
+        import os
+        self.side_stream = torch.cuda.Stream(device=self.device) if os.environ.get("STCGAN_SIDE_STREAM", "1") != "0" else None
+        for rt in self.rt.values():
+            rt.side_stream = self.side_stream
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})

@@ -238,6 +238,31 @@ class _NetRuntimeBase:
     def device(self):
         return self.convs[0].weight.device
 
+    # ---- weight gradients on a side stream ----------------------------------------------------------------------
+    # A layer's wgrad only feeds the optimiser, while its dgrad feeds the rest of the backward chain: with `side_stream`
+    # set (the engine does), every wgrad launch is forked onto that stream right after the kernels that produced its
+    # operands, and the backward pass joins it at its end.  The two kernel families then share the SMs, which fills the
+    # partial waves and per-kernel ramps each of them leaves idle on its own.  Works in plain streams and under CUDA-graph
+    # capture (fork / join become graph edges).  wgrad kernels only accumulate into the preallocated flat gradient buffer
+    # (no allocation on the side stream); their operand tensors are kept alive until the join (`keep`).
+    side_stream = None
+
+    def _wgrad_async(self, ws, fn, *tensors):
+        side = self.side_stream
+        if side is None:
+            fn()
+            return
+        ws.setdefault("keep", []).extend(t for t in tensors if t is not None)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        ws["forked"] = True
+
+    def _join_side(self, ws):
+        if ws.pop("forked", False):
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        ws.pop("keep", None)
+
     def pack_sources(self, sources):
         """The torch.cat of cgan.py:281-289,321-324 as ONE packed NHWC tensor: ("b", zero-bordered 8-channel tensor) when
         the first layer runs on the thin tensor-core path, else ("p", cpad-channel tensor).  The result only depends on the
@@ -403,12 +428,12 @@ class GeneratorRuntime(_NetRuntimeBase):
         if up.thin == "coutT":
             g_b = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt, cpad=8, border=1)
             if param_grads:
-                up.wgrad(ws["cat"][1], None, g_bordered=g_b)
+                self._wgrad_async(ws, lambda: up.wgrad(ws["cat"][1], None, g_bordered=g_b), g_b)
             dcat = up.dgrad(None, *s[1], g_bordered=g_b)
         else:
             g = ops.out_act_bwd(ACT_TANH, ws["out"], dout, dt)
             if param_grads:
-                up.wgrad(ws["cat"][1], g)
+                self._wgrad_async(ws, lambda: up.wgrad(ws["cat"][1], g), g)
             dcat = up.dgrad(g, *s[1])
         # ---- decoder, outside-in
         for k in range(2, L + 1):
@@ -418,7 +443,7 @@ class GeneratorRuntime(_NetRuntimeBase):
             bn.backward(uy, sc, training, dcat[..., C[k - 1]:], ACT_RELU, None, ACT_NONE, guy, param_grads, zero_acc=False)
             x_in = ws["cat"][k] if k < L else ws["a"][L]
             if param_grads:
-                up.wgrad(x_in, guy)
+                self._wgrad_async(ws, lambda up=up, x_in=x_in, guy=guy: up.wgrad(x_in, guy), guy)
             dcat_prev, dcat = dcat, up.dgrad(guy, *s[k])
             ws.setdefault("dcat", {})[k - 1] = dcat_prev
         dcats = ws["dcat"]
@@ -440,7 +465,8 @@ class GeneratorRuntime(_NetRuntimeBase):
             thin_in = k == 1 and ws["inp_b"] is not None
             x_in = ws["a"][k - 1] if k > 1 else (None if thin_in else ws["inp"][..., :self.cin])
             if param_grads:
-                down.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None)
+                self._wgrad_async(ws, lambda down=down, x_in=x_in, gy=gy, thin_in=thin_in:
+                                  down.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None), gy)
             if k > 1:
                 da = down.dgrad(gy, *s[k - 1])
             elif need_input_grad:
@@ -450,7 +476,9 @@ class GeneratorRuntime(_NetRuntimeBase):
                 else:
                     dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
                     down.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                self._join_side(ws)
                 return dinp
+        self._join_side(ws)
         return None
 
 
@@ -537,11 +565,12 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                 gy = g
             if i == nl - 1 and g_b is not None:
                 if param_grads:
-                    conv.wgrad(x_in, None, g_bordered=g_b)
+                    self._wgrad_async(ws, lambda conv=conv, x_in=x_in: conv.wgrad(x_in, None, g_bordered=g_b), g_b)
                 g = conv.dgrad(None, *s[i], g_bordered=g_b)
                 continue
             if param_grads:
-                conv.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None, bias_done=bias_done)
+                self._wgrad_async(ws, lambda conv=conv, x_in=x_in, gy=gy, thin_in=thin_in, bias_done=bias_done:
+                                  conv.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None, bias_done=bias_done), gy)
             if i > 0:
                 g = conv.dgrad(gy, *s[i])
             elif need_input_grad:
@@ -551,5 +580,7 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                 else:
                     dinp = torch.empty((n, s[0][0], s[0][1], self.cpad), dtype=dt, device=dev)
                     conv.dgrad(gy, *s[0], out=dinp[..., :self.cin])
+                self._join_side(ws)
                 return dinp
+        self._join_side(ws)
         return None

@@ -18,6 +18,8 @@ nets = dict(G1=S.UnetGenerator(3, 1), G2=S.UnetGenerator(4, 3), D1=S.NLayerDiscr
 for n in nets.values():
     n.to(dev).train()
 eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"])
+for rt in eng.rt.values():
+    rt.side_stream = None          # per-launch event intervals need every kernel on the timing stream
 x, m, y = (t.contiguous().to(dev) for t in O.make_istd_batch(batch, H, W))
 for _ in range(3):
     eng.train_step(x, m, y)
