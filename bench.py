@@ -152,6 +152,8 @@ def instrumented_breakdown(eng, x, m, y):
     # the instrumented step runs every kernel on ONE stream (the production step forks the weight-gradient kernels onto a
     # side stream, where per-launch event intervals on the main stream would not bracket them)
     side = {k: rt.side_stream for k, rt in eng.rt.items()}
+    lanes = eng.lanes.streams
+    eng.lanes.streams = []
     for rt in eng.rt.values():
         rt.side_stream = None
     try:
@@ -167,6 +169,7 @@ def instrumented_breakdown(eng, x, m, y):
             setattr(ops, name, fn)
         for k, rt in eng.rt.items():
             rt.side_stream = side[k]
+        eng.lanes.streams = lanes
     fam = {}
     for name, fl, e0, e1 in rec:
         t, f, c = fam.get(name, (0.0, 0.0, 0))
@@ -273,7 +276,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": "ST-CGAN full train step 256x256, 16 images/GPU (BASELINE configs[1]; cgan.py:274-351, VisualLoss off, "
                                "MSE adversarial loss as executed, Adam beta=(0.5,0.999)), bf16 activations/weights, fp32 master+Adam",
                    "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}", "l2": "per-step working set (>2 GB of activations "
-                   "and weights) exceeds the 126 MB L2; no explicit flush", "cuda_graph": True, "streams": "weight-gradient kernels on a side stream (fork/join inside the graph)",
+                   "and weights) exceeds the 126 MB L2; no explicit flush", "cuda_graph": True, "streams": "D1 / D2 / generator chains on three streams, weight-gradient kernels on side streams (fork/join inside the graph)",
                    "algorithmic_gflop_per_image": O.train_step_flops(H, W) / 1e9},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
                 "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": 1e3 * dt_e2e / args.steps},

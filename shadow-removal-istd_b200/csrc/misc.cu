@@ -570,10 +570,12 @@ __global__ void adam_tick_kernel(float* __restrict__ hyper) {
   hyper[7] = (float)(1.0 / sqrt(bc2));
 }
 
-int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st) {
+static int adam_update(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, int tick, cudaStream_t st) {
   if (nblocks <= 0) return STCGAN_EINVAL;
-  launch_k(adam_tick_kernel, 1, 1, 0, st, hyper);
-  ++g_launches;
+  if (tick) {
+    launch_k(adam_tick_kernel, 1, 1, 0, st, hyper);
+    ++g_launches;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(adam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ADAM_SMEM);
@@ -582,6 +584,18 @@ int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblock
   }
   launch_k(adam_kernel, nblocks, 256, ADAM_SMEM, st, table, blocks, hyper);
   return finish_launch();
+}
+
+int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st) {
+  return adam_update(table, blocks, nblocks, hyper, 1, st);
+}
+
+// a sub-range of the block list (the tensors of one network): `tick` advances the step counter / bias corrections and
+// must be set on exactly one of the partial launches of a step -- the first one, the others must be ordered after it
+int adam_step_range(const stcgan_adam_tensor* table, const int32_t* blocks, int first_block, int nblocks, float* hyper, int tick,
+                    cudaStream_t st) {
+  if (first_block < 0) return STCGAN_EINVAL;
+  return adam_update(table, blocks + 2 * (long long)first_block, nblocks, hyper, tick, st);
 }
 
 // ---------------------------------------------------------------------------------------------

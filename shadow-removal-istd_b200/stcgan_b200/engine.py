@@ -27,6 +27,34 @@ from .optim import FusedAdam
 SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss")
 
 
+class _Lanes:
+    """Two extra streams for the D1 / D2 chains of a phase.  fork(): the lanes wait for everything issued so far on the
+    current stream; lane(i): context manager that issues on lane i (or on the current stream when disabled);
+    lane_wait(i): lane i additionally waits for what the current stream has issued since; join(): the current stream waits
+    for both lanes."""
+
+    def __init__(self, streams):
+        self.streams = streams
+
+    def fork(self):
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def lane(self, i):
+        import contextlib
+        return torch.cuda.stream(self.streams[i]) if self.streams else contextlib.nullcontext()
+
+    def lane_wait(self, i):
+        if self.streams:
+            self.streams[i].wait_stream(torch.cuda.current_stream())
+
+    def join(self):
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+
+
 class GradientSync:
     """Data-parallel gradient exchange: SUM all-reduce of named flat gradient buffers over a process group (NCCL on the
     GPUs, gloo in the CPU tests); the 1/world scale is applied inside the optimiser kernel.  `reduce(names, blocking,
@@ -81,11 +109,20 @@ class STCGANEngine:
             rt.ensure_packed()
             rt.alloc_grads()
         self.device = self.rt["G1"].device()
-        # weight-gradient kernels run on a side stream, concurrently with the dgrad / BatchNorm chain (nets._wgrad_async)
+        # Concurrency inside the step (STCGAN_CONCURRENCY=0 turns all of it off, STCGAN_SIDE_STREAM=0 only the first):
+        #  * every network's weight-gradient kernels run on its own side stream, next to the dgrad / BatchNorm chain
+        #    (nets._wgrad_async);
+        #  * the D1 chain and the D2 chain of each phase run on two lanes next to the generator chain on the main stream --
+        #    they only meet at the loss kernels (cgan.py:281-302, 321-348 have no other cross-dependency).
+        # All forks and joins are stream events, so the same code runs eagerly and under CUDA-graph capture.
         import os
-        self.side_stream = torch.cuda.Stream(device=self.device) if os.environ.get("STCGAN_SIDE_STREAM", "1") != "0" else None
-        for rt in self.rt.values():
-            rt.side_stream = self.side_stream
+        conc = os.environ.get("STCGAN_CONCURRENCY", "1") != "0"
+        side = conc and os.environ.get("STCGAN_SIDE_STREAM", "1") != "0"
+        mk = lambda: torch.cuda.Stream(device=self.device)
+        self.side_streams = {k: (mk() if side else None) for k in ("G", "D1", "D2")}
+        for k, r in self.rt.items():
+            r.side_stream = self.side_streams["G" if k in ("G1", "G2") else k]
+        self.lanes = _Lanes([mk(), mk()] if conc else [])
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
@@ -110,19 +147,30 @@ class STCGANEngine:
         real, fake = 1.0, (-1.0 if cfg.ls else 0.0)
         newg = lambda t: torch.empty_like(t)
         # ================= D phase (cgan.py:278-305) =================
+        L = self.lanes
         rt["D1"].zero_grads(); rt["D2"].zero_grads()
-        # every distinct input concatenation (cgan.py:281-289, 321-324) is packed once per step and shared
-        pk_xm = rt["D1"].pack_sources([x, m])
-        c1r, w1r = rt["D1"].forward([x, m], True, packed=pk_xm)
+        # every distinct input concatenation (cgan.py:281-289, 321-324) is packed once per step and shared.
+        # lane 0: D1 real -> D1 fake, lane 1: D2 real -> D2 fake, main stream: G1 -> G2 (each D keeps its two passes in the
+        # reference order on one stream: the BatchNorm running statistics are order-dependent)
+        L.fork()
+        with L.lane(0):
+            pk_xm = rt["D1"].pack_sources([x, m])
+            c1r, w1r = rt["D1"].forward([x, m], True, packed=pk_xm)
+        with L.lane(1):
+            pk_xmy = rt["D2"].pack_sources([x, m, y])
+            c2r, w2r = rt["D2"].forward([x, m, y], True, packed=pk_xmy)
         mp, wg1 = rt["G1"].forward([x], True)
         pk_xmp = rt["D1"].pack_sources([x, mp])
-        c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)
-        pk_xmy = rt["D2"].pack_sources([x, m, y])
-        c2r, w2r = rt["D2"].forward([x, m, y], True, packed=pk_xmy)
+        L.lane_wait(0)
+        with L.lane(0):
+            c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)
         share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
         yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
         pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
-        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)
+        L.lane_wait(1)
+        with L.lane(1):
+            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)
+        L.join()
         self.last = dict(m_pred=mp, y_pred=yp)
         self.losses.zero_()
         d1r, d1f, d2r, d2f = newg(c1r), newg(c1f), newg(c2r), newg(c2f)
@@ -132,18 +180,27 @@ class STCGANEngine:
             dict(kind=kind, a=c2r, grad=d2r, target=real, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
             dict(kind=kind, a=c2f, grad=d2f, target=fake, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
         ], self.losses)
-        rt["D1"].backward(w1r, d1r, False); rt["D1"].backward(w1f, d1f, False)
-        rt["D2"].backward(w2r, d2r, False); rt["D2"].backward(w2f, d2f, False)
+        L.fork()
+        with L.lane(0):
+            rt["D1"].backward(w1r, d1r, False); rt["D1"].backward(w1f, d1f, False)
+        with L.lane(1):
+            rt["D2"].backward(w2r, d2r, False); rt["D2"].backward(w2f, d2f, False)
+        L.join()
         del w1r, w1f, w2r, w2f
         yield ("D1", "D2"), True                              # blocking: optim_D needs the reduced gradients
         self.optim_D.step()                                   # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
-        if not cfg.skip_dead_real_passes:
-            rt["D1"].forward([x, m], True, packed=pk_xm)      # cgan.py:321 (BatchNorm running-stat side effect only)
-            rt["D2"].forward([x, m, y], True, packed=pk_xmy)  # cgan.py:323
-        c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)        # cgan.py:322
-        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)  # cgan.py:324
+        L.fork()
+        with L.lane(0):
+            if not cfg.skip_dead_real_passes:
+                rt["D1"].forward([x, m], True, packed=pk_xm)      # cgan.py:321 (BatchNorm running-stat side effect only)
+            c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)        # cgan.py:322
+        with L.lane(1):
+            if not cfg.skip_dead_real_passes:
+                rt["D2"].forward([x, m, y], True, packed=pk_xmy)  # cgan.py:323
+            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)  # cgan.py:324
+        L.join()
         dm, dy, d1f, d2f = newg(mp), newg(yp), newg(c1f), newg(c2f)
         ops.fused_loss([
             dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),
@@ -151,17 +208,32 @@ class STCGANEngine:
             dict(kind=kind, a=c1f, grad=d1f, target=real, weight=cfg.lambda2, loss_weight=1.0, slot=2),
             dict(kind=kind, a=c2f, grad=d2f, target=real, weight=cfg.lambda3, loss_weight=1.0, slot=3),
         ], self.losses)
-        di2 = rt["D2"].backward(w2f, d2f, True, param_grads=False)      # dgrad only: D is frozen (cgan.py:317-318)
+        L.fork()
+        with L.lane(0):
+            di1 = rt["D1"].backward(w1f, d1f, True, param_grads=False)  # dgrad only: D is frozen (cgan.py:317-318)
+        di2 = rt["D2"].backward(w2f, d2f, True, param_grads=False)
         ops.unpack_input_grad(di2, 4, 3, dy, True)
         ops.unpack_input_grad(di2, 3, 1, dm, True)
-        di1 = rt["D1"].backward(w1f, d1f, True, param_grads=False)
+        L.join()
         ops.unpack_input_grad(di1, 3, 1, dm, True)
         dig2 = rt["G2"].backward(wg2, dy, True)
         ops.unpack_input_grad(dig2, 3, 1, dm, True)           # G2's input gradient, mask channel (cgan.py:286)
         yield ("G2",), False                                  # async: overlaps G1's backward
+        split = self.world == 1 and bool(L.streams)
+        if split:
+            # single GPU: G2's gradients are final, so G2's share of optim_G.step (cgan.py:351; an HBM-bound stream over
+            # 28 B/parameter) runs on a lane underneath G1's tensor-bound backward pass
+            L.fork()
+            with L.lane(0):
+                self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False)
         rt["G1"].backward(wg1, dm, False)
+        if split:
+            L.join()
         yield ("G1",), True
-        self.optim_G.step()                                   # cgan.py:351
+        if split:
+            self.optim_G.step_partial(list(self.nets["G1"].parameters()), tick=False, last=True)
+        else:
+            self.optim_G.step()                               # cgan.py:351
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step
 

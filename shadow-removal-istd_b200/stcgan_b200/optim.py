@@ -73,7 +73,7 @@ class FusedAdam(torch.optim.Optimizer):
     def _build_table(self, group):
         chunk = _lib.load().stcgan_adam_chunk()
         tile = _lib.load().stcgan_adam_tile()
-        entries, blocks, keep, fused = [], [], [], []
+        entries, blocks, keep, fused, ranges = [], [], [], [], {}
         for p in group["params"]:
             gd = self._grad_of(p)
             if gd is None:
@@ -97,6 +97,7 @@ class FusedAdam(torch.optim.Optimizer):
                                            st["exp_avg_sq"].data_ptr(), p.numel(), d0, d1, p1, p2))
             keep.append((p, g, st))
             nblk = (d0 // tile) * (d1 // tile) if p1 is not None else (p.numel() + chunk - 1) // chunk
+            ranges[id(p)] = (len(blocks), nblk)
             blocks += [(ti, c) for c in range(nblk)]
         if not entries:
             return None
@@ -109,7 +110,7 @@ class FusedAdam(torch.optim.Optimizer):
         hyper_host = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(self.grad_scale), steps_done, 0.0, 0.0]
         hyper = torch.tensor(hyper_host, dtype=torch.float32, device=dev)
         return dict(sig=self._signature(group), table=table, blocks=blk, nblocks=len(blocks), keep=keep,
-                    hyper=hyper, hyper_host=hyper_host, fused=fused)
+                    hyper=hyper, hyper_host=hyper_host, fused=fused, ranges=ranges)
 
     def _sync_hyper(self, group, t):
         """Push lr / grad_scale changes (ExponentialLR steps once per epoch, src/cgan.py:383-384) to the device."""
@@ -131,6 +132,35 @@ class FusedAdam(torch.optim.Optimizer):
             if t is not None:
                 for _, _, st in t["keep"]:
                     st["step"] += 1
+
+    @torch.no_grad()
+    def step_partial(self, params, tick, last):
+        """Update only `params` (a contiguous run of this optimiser's single param group, e.g. one network's parameters).
+        One optimiser step = several partial calls covering all parameters: `tick=True` on the first (advances the step
+        counter on the device), `last=True` on the final one (host-side bookkeeping).  Calls after the first must be
+        stream-ordered after it."""
+        lib = _lib.load()
+        self.prepare()
+        if len(self.param_groups) != 1:
+            raise RuntimeError("step_partial expects a single param group")
+        group, t = self.param_groups[0], self._tables.get(0)
+        if t is None:
+            return
+        self._sync_hyper(group, t)
+        rs = [t["ranges"][id(p)] for p in params if id(p) in t["ranges"]]
+        first = min(r[0] for r in rs)
+        end = max(r[0] + r[1] for r in rs)
+        if sum(r[1] for r in rs) != end - first:
+            raise RuntimeError("step_partial: the parameters do not form a contiguous run of the param group")
+        _lib.check(lib.stcgan_adam_step_range(t["table"].data_ptr(), t["blocks"].data_ptr(), first, end - first,
+                                              t["hyper"].data_ptr(), int(tick), torch.cuda.current_stream().cuda_stream),
+                   "stcgan_adam_step_range")
+        if last:
+            for p, _, st in t["keep"]:
+                st["step"] += 1
+                torch.autograd.graph.increment_version(p)
+            for conv in t["fused"]:
+                conv.mark_packed()
 
     @torch.no_grad()
     def step(self, closure=None):
