@@ -270,9 +270,11 @@ int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blo
                      float* dev_hyper, void* stream);
 /* the same update for the blocks [first_block, first_block + nblocks) of dev_blocks only (e.g. the tensors of one network, so
  * that its update can start while another network's backward pass is still running).  tick != 0 advances steps_done and the
- * bias corrections: set it on exactly one partial launch per optimiser step, ordered before the others. */
+ * bias corrections: set it on exactly one partial launch per optimiser step, ordered before the others.
+ * max_ctas > 0 caps the grid (the CTAs then loop over the blocks): a launch that runs underneath compute-bound kernels of
+ * another stream should not take every SM's shared memory. */
 int stcgan_adam_step_range(const stcgan_adam_tensor* dev_table, const int32_t* dev_blocks, int first_block, int nblocks,
-                           float* dev_hyper, int tick, void* stream);
+                           float* dev_hyper, int tick, int max_ctas, void* stream);
 /* elements per block chunk used by stcgan_adam_step (host helper for building dev_blocks) */
 int stcgan_adam_chunk(void);
 /* tile edge T (in (d0, d1) pairs) of tensors whose packed bf16 copies are refreshed by stcgan_adam_step */

@@ -64,7 +64,7 @@ int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H
 int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st);
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st);
 int adam_step_range(const stcgan_adam_tensor* table, const int32_t* blocks, int first_block, int nblocks, float* hyper, int tick,
-                    cudaStream_t st);
+                    int max_ctas, cudaStream_t st);
 int float2uint(const float* in, long long n, uint8_t* out, cudaStream_t st);
 int u8_to_nchw(const uint8_t* in, int N, int H, int W, int C, float* out, cudaStream_t st);
 int float2uint_hwc(const float* in, int N, int C, int H, int W, uint8_t* out, cudaStream_t st);
@@ -286,9 +286,9 @@ int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blo
 }
 
 int stcgan_adam_step_range(const stcgan_adam_tensor* dev_table, const int32_t* dev_blocks, int first_block, int nblocks,
-                           float* dev_hyper, int tick, void* stream) {
+                           float* dev_hyper, int tick, int max_ctas, void* stream) {
   STCGAN_REQUIRE(dev_table && dev_blocks && dev_hyper);
-  return adam_step_range(dev_table, dev_blocks, first_block, nblocks, dev_hyper, tick, as_stream(stream));
+  return adam_step_range(dev_table, dev_blocks, first_block, nblocks, dev_hyper, tick, max_ctas, as_stream(stream));
 }
 
 int stcgan_adam_chunk(void) { return 256 * 16; }

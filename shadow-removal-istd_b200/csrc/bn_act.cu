@@ -424,7 +424,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
 }
 
 // pass 2: dy = A*dz - B - (y - mean)*Cc  with A = gamma*invstd, B = A*mean(dz), Cc = A*invstd^2*mean(dz*(y-mean))
-//         (training);  dy = A*dz (eval);  dy = dz (no BatchNorm).  dgamma += invstd*acc[1], dbeta += acc[0] (block 0).
+//         (training);  dy = A*dz (eval);  dy = dz (no BatchNorm).  dgamma += invstd*acc[1], dbeta += acc[0] (block 0,
+//         atomically: the real and the fake pass of a discriminator may run their backward passes concurrently).
 //         The per-channel coefficients are derived once per block into shared memory (sum over the statistic slots).
 //         dbias (optional, layers with a conv bias and no BatchNorm): dbias[c] += sum_p dy[p, c].
 template <typename T>
@@ -452,12 +453,12 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
         for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { a0 += acc[(2 * k) * C + c]; a1 += acc[(2 * k + 1) * C + c]; }
         kC = kA * invstd * invstd * (float)(a1 * invP);
         kB = kA * (float)(a0 * invP) - mean * kC;        // folded: -(y - mean)*kC = -y*kC + mean*kC
-        if (blockIdx.x == 0 && dgamma) { dgamma[c] += (float)(a1 * (double)invstd); dbeta[c] += (float)a0; }
+        if (blockIdx.x == 0 && dgamma) { atomicAdd(&dgamma[c], (float)(a1 * (double)invstd)); atomicAdd(&dbeta[c], (float)a0); }
       } else if (blockIdx.x == 0 && dgamma && acc) {
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { a0 += acc[(2 * k) * C + c]; a1 += acc[(2 * k + 1) * C + c]; }
-        dgamma[c] += (float)(a1 * (double)invstd); dbeta[c] += (float)a0;
+        atomicAdd(&dgamma[c], (float)(a1 * (double)invstd)); atomicAdd(&dbeta[c], (float)a0);
       }
     }
     coef[c] = sc; coef[C + c] = sh; coef[2 * C + c] = kA; coef[3 * C + c] = kB; coef[4 * C + c] = kC;

@@ -459,13 +459,15 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {   // read-once d
 }
 
 __global__ void __launch_bounds__(256)
-adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restrict__ blocks,
+adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restrict__ blocks, int nblocks,
             const float* __restrict__ hyper) {
   pdl_prologue();
   extern __shared__ __align__(16) uint8_t adam_smem[];
   const float step_size = hyper[6], inv_bc2_sqrt = hyper[7], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3],
               grad_scale = hyper[4];
-  const int ti = blocks[2 * blockIdx.x], chunk = blocks[2 * blockIdx.x + 1];
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+  __syncthreads();       // the staging tiles of the previous block of work are free
+  const int ti = blocks[2 * blk], chunk = blocks[2 * blk + 1];
   const stcgan_adam_tensor t = table[ti];
   const long long base = (long long)chunk * ADAM_CHUNK;
   if (t.d0 > 0 && t.p1 != nullptr) {
@@ -539,7 +541,7 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
     // packed gradients without bf16 refresh (thin layers): one thread owns one (d0,d1) pair = 16 contiguous parameters
     const long long plane = (long long)t.d0 * t.d1;
     const long long r = base / 16 + threadIdx.x;
-    if (r >= plane) return;
+    if (r >= plane) continue;
     float* pp = t.p + r * 16; float* pm = t.m + r * 16; float* pv = t.v + r * 16;
 #pragma unroll 4
     for (int k = 0; k < 16; ++k) {
@@ -557,6 +559,7 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
       t.p[i] = p; t.m[i] = m; t.v[i] = v;
     }
   }
+  }
 }
 
 // steps_done += 1; bias corrections in double like torch (1 - beta^t)
@@ -570,7 +573,8 @@ __global__ void adam_tick_kernel(float* __restrict__ hyper) {
   hyper[7] = (float)(1.0 / sqrt(bc2));
 }
 
-static int adam_update(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, int tick, cudaStream_t st) {
+static int adam_update(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, int tick, int max_ctas,
+                       cudaStream_t st) {
   if (nblocks <= 0) return STCGAN_EINVAL;
   if (tick) {
     launch_k(adam_tick_kernel, 1, 1, 0, st, hyper);
@@ -582,20 +586,21 @@ static int adam_update(const stcgan_adam_tensor* table, const int32_t* blocks, i
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  launch_k(adam_kernel, nblocks, 256, ADAM_SMEM, st, table, blocks, hyper);
+  const int grid = (max_ctas > 0 && max_ctas < nblocks) ? max_ctas : nblocks;
+  launch_k(adam_kernel, grid, 256, ADAM_SMEM, st, table, blocks, nblocks, hyper);
   return finish_launch();
 }
 
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st) {
-  return adam_update(table, blocks, nblocks, hyper, 1, st);
+  return adam_update(table, blocks, nblocks, hyper, 1, 0, st);
 }
 
 // a sub-range of the block list (the tensors of one network): `tick` advances the step counter / bias corrections and
 // must be set on exactly one of the partial launches of a step -- the first one, the others must be ordered after it
 int adam_step_range(const stcgan_adam_tensor* table, const int32_t* blocks, int first_block, int nblocks, float* hyper, int tick,
-                    cudaStream_t st) {
+                    int max_ctas, cudaStream_t st) {
   if (first_block < 0) return STCGAN_EINVAL;
-  return adam_update(table, blocks + 2 * (long long)first_block, nblocks, hyper, tick, st);
+  return adam_update(table, blocks + 2 * (long long)first_block, nblocks, hyper, tick, max_ctas, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -54,7 +54,9 @@ struct alignas(64) TapGemmParams {
   // (fp32 over the 128 rows of a tile, then fp64 atomics) into bn_acc[slot][2][bn_c], slot = CTA index % STCGAN_BN_SLOTS
   double* bn_acc;
   int bn_c;
-  int dbg_mode;            // timing experiments only (STCGAN_TC_DBGMODE): bit 0 = skip the MMAs, bit 1 = skip the TMA loads
+  int dbg_mode;            // timing experiments only (STCGAN_TC_DBGMODE): bit 0 = skip the MMAs, bit 1 = skip the TMA loads,
+                           // bit 2 = fetch the weight tile as ONE contiguous bulk copy (wrong data: timing of a tile-major layout)
+  const void* wp_raw;
 };
 
 __device__ __forceinline__ long long gtime() {
@@ -157,7 +159,11 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
           else {
             mbar_expect_tx(&full_bar[s], SM::STAGE_BYTES);
             tma_load_4d(am, &full_bar[s], a_dst, kc * TC_BK, cxj, cyj, n0);
-            tma_load_2d(&P.bmap, &full_bar[s], a_dst + SM::A_BYTES, kc * TC_BK, wrowj);
+            if (P.dbg_mode & 4)
+              bulk_load_1d(a_dst + SM::A_BYTES, static_cast<const uint8_t*>(P.wp_raw) + (size_t)((j * kchunks + kc) % 32) * SM::B_BYTES,
+                           SM::B_BYTES, &full_bar[s]);
+            else
+              tma_load_2d(&P.bmap, &full_bar[s], a_dst + SM::A_BYTES, kc * TC_BK, wrowj);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -1001,8 +1007,8 @@ static int pair_mode() {
 // allows it; measured on B200 it is parity-green but 12 % slower on the conv launches of a train step than 128x128 tiles
 // with 3 stages, so the default stays 128.
 static int bn_select(int Nout) {
-  static int wide = -1;
-  if (wide < 0) { const char* e = getenv("STCGAN_TC_BN256"); wide = (e && e[0] == '1') ? 1 : 0; }
+  int wide;
+  { const char* e = getenv("STCGAN_TC_BN256"); wide = (e && e[0] == '1') ? 1 : 0; }
   if (wide && Nout % 256 == 0) return 256;
   return Nout % 128 == 0 ? 128 : 64;
 }
@@ -1011,6 +1017,11 @@ static int deep_ring_mode() {     // STCGAN_TC_DEEP=0 disables the 6/8-stage var
   static int v = -1;
   if (v < 0) { const char* e = getenv("STCGAN_TC_DEEP"); v = (e && e[0] == '0') ? 0 : 1; }
   return v;
+}
+
+static int bn256_stages() {     // STCGAN_TC_BN256_STAGES=2: two CTAs per SM with two stages each; default 4 stages, one CTA
+  const char* e = getenv("STCGAN_TC_BN256_STAGES");
+  return (e && e[0] == '2') ? 2 : 4;
 }
 
 static int persistent_mode() {
@@ -1080,6 +1091,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   P.nout_real = Nout; P.y32 = y32;
   P.bn_acc = bn_acc; P.bn_c = Nout;
   { const char* e = getenv("STCGAN_TC_DBGMODE"); P.dbg_mode = e ? atoi(e) : 0; }
+  P.wp_raw = wp;
   const int n_rows = thin_n ? 16 : Nout;     // rows per tap in the packed weight matrix
   int GH = 0, GW = 0;
   for (int c = 0; c < g.nclass; ++c) {
@@ -1181,7 +1193,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);
   }
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
-  if (BN == 256) return launch_tapgemm<256, 2>(P, grid, st);
+  if (BN == 256) return bn256_stages() == 4 ? launch_tapgemm<256, 4>(P, grid, st) : launch_tapgemm<256, 2>(P, grid, st);
   // launches that leave at most one CTA per SM get a deeper ring instead of a second resident CTA: with 3 stages a lone CTA
   // covers only ~96 KB of the ~170 KB that must be in flight to feed the tensor pipe (measured 0.40 us per 128x128x64 step
   // against 0.21 us with two resident CTAs)

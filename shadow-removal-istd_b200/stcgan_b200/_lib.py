@@ -74,7 +74,7 @@ SIGNATURES = {
     "stcgan_out_act_bwd": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_fused_loss": (_i, [C.POINTER(LossTerm), _i, _p, _p]),
     "stcgan_adam_step": (_i, [_p, _p, _i, _p, _p]),
-    "stcgan_adam_step_range": (_i, [_p, _p, _i, _i, _p, _i, _p]),
+    "stcgan_adam_step_range": (_i, [_p, _p, _i, _i, _p, _i, _i, _p]),
     "stcgan_adam_chunk": (_i, []),
     "stcgan_adam_tile": (_i, []),
     "stcgan_float2uint_hwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),

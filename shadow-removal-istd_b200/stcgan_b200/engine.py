@@ -17,6 +17,7 @@ bucket while G1's backward is still running.  The whole step can be captured int
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -28,7 +29,7 @@ SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss")
 
 
 class _Lanes:
-    """Two extra streams for the D1 / D2 chains of a phase.  fork(): the lanes wait for everything issued so far on the
+    """Extra streams for the D1 / D2 chains of a phase (lanes 0, 1; lanes 2, 3 take the second backward pass of each).  fork(): the lanes wait for everything issued so far on the
     current stream; lane(i): context manager that issues on lane i (or on the current stream when disabled);
     lane_wait(i): lane i additionally waits for what the current stream has issued since; join(): the current stream waits
     for both lanes."""
@@ -43,7 +44,7 @@ class _Lanes:
 
     def lane(self, i):
         import contextlib
-        return torch.cuda.stream(self.streams[i]) if self.streams else contextlib.nullcontext()
+        return torch.cuda.stream(self.streams[i % len(self.streams)]) if self.streams else contextlib.nullcontext()
 
     def lane_wait(self, i):
         if self.streams:
@@ -115,14 +116,13 @@ class STCGANEngine:
         #  * the D1 chain and the D2 chain of each phase run on two lanes next to the generator chain on the main stream --
         #    they only meet at the loss kernels (cgan.py:281-302, 321-348 have no other cross-dependency).
         # All forks and joins are stream events, so the same code runs eagerly and under CUDA-graph capture.
-        import os
         conc = os.environ.get("STCGAN_CONCURRENCY", "1") != "0"
         side = conc and os.environ.get("STCGAN_SIDE_STREAM", "1") != "0"
         mk = lambda: torch.cuda.Stream(device=self.device)
         self.side_streams = {k: (mk() if side else None) for k in ("G", "D1", "D2")}
         for k, r in self.rt.items():
             r.side_stream = self.side_streams["G" if k in ("G1", "G2") else k]
-        self.lanes = _Lanes([mk(), mk()] if conc else [])
+        self.lanes = _Lanes([mk(), mk(), mk(), mk()] if conc else [])
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
@@ -181,10 +181,15 @@ class STCGANEngine:
             dict(kind=kind, a=c2f, grad=d2f, target=fake, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
         ], self.losses)
         L.fork()
+        # the four backward passes only meet in atomic accumulations (packed weight gradients, BatchNorm / bias gradients)
         with L.lane(0):
-            rt["D1"].backward(w1r, d1r, False); rt["D1"].backward(w1f, d1f, False)
+            rt["D1"].backward(w1r, d1r, False)
         with L.lane(1):
-            rt["D2"].backward(w2r, d2r, False); rt["D2"].backward(w2f, d2f, False)
+            rt["D2"].backward(w2r, d2r, False)
+        with L.lane(2):
+            rt["D1"].backward(w1f, d1f, False)
+        with L.lane(3):
+            rt["D2"].backward(w2f, d2f, False)
         L.join()
         del w1r, w1f, w2r, w2f
         yield ("D1", "D2"), True                              # blocking: optim_D needs the reduced gradients
@@ -225,7 +230,8 @@ class STCGANEngine:
             # 28 B/parameter) runs on a lane underneath G1's tensor-bound backward pass
             L.fork()
             with L.lane(0):
-                self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False)
+                self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False,
+                                          max_ctas=int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148")))
         rt["G1"].backward(wg1, dm, False)
         if split:
             L.join()

@@ -134,7 +134,7 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] += 1
 
     @torch.no_grad()
-    def step_partial(self, params, tick, last):
+    def step_partial(self, params, tick, last, max_ctas=0):
         """Update only `params` (a contiguous run of this optimiser's single param group, e.g. one network's parameters).
         One optimiser step = several partial calls covering all parameters: `tick=True` on the first (advances the step
         counter on the device), `last=True` on the final one (host-side bookkeeping).  Calls after the first must be
@@ -153,7 +153,8 @@ class FusedAdam(torch.optim.Optimizer):
         if sum(r[1] for r in rs) != end - first:
             raise RuntimeError("step_partial: the parameters do not form a contiguous run of the param group")
         _lib.check(lib.stcgan_adam_step_range(t["table"].data_ptr(), t["blocks"].data_ptr(), first, end - first,
-                                              t["hyper"].data_ptr(), int(tick), torch.cuda.current_stream().cuda_stream),
+                                              t["hyper"].data_ptr(), int(tick), int(max_ctas),
+                                              torch.cuda.current_stream().cuda_stream),
                    "stcgan_adam_step_range")
         if last:
             for p, _, st in t["keep"]:
