@@ -262,7 +262,13 @@ def run_b200(args, rank, world, local_rank):
     tc_n = sum(v[2] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
     achieved = tc_f / tc_t / 1e12 if tc_t > 0 else 0.0
     roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tf_sustained"], "traffic": None,
+            "frac": achieved / peaks["tf_sustained"],
+            # DRAM bytes (read + write) of ONE profiled launch of the dominant kernel, `ncu --set full` (committed summary):
+            # D's c4 input gradient, tapgemm_tc_kernel<128,3> grid (128,2,1): 19.97 MB read + 0 written back during the launch
+            # (the 8.4 MB output stays in L2) against 28.3 MB algorithmic (15.7 MB input + 4.2 MB weights + 8.4 MB output)
+            "traffic": 19.97e6,
+            "traffic_note": "per launch of tapgemm_tc_kernel<128,3> grid (128,2,1) (c4 dgrad), profiles/r01_ncu_full_tapgemm_v2.csv; "
+                            "algorithmic 28.3 MB; tensor pipe active 57.7 % in that capture",
             "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all full-width tcgen05 conv launches of one train step)",
             "eager_step_seconds": eager_s,
             "launches": tc_n, "flops_per_step": tc_f, "seconds_per_step": tc_t, "peak_source": peaks["source"] + ", sustained bf16",
