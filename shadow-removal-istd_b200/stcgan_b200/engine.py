@@ -59,8 +59,9 @@ class _Lanes:
 class GradientSync:
     """Data-parallel gradient exchange: SUM all-reduce of named flat gradient buffers over a process group (NCCL on the
     GPUs, gloo in the CPU tests); the 1/world scale is applied inside the optimiser kernel.  `reduce(names, blocking,
-    pending)` launches the collectives asynchronously; a blocking call also waits for everything pending, which is how
-    the G2 bucket overlaps G1's backward while D's bucket gates `optim_D.step` (src/cgan.py:305)."""
+    pending, wait=())` launches the collectives asynchronously; `wait` names earlier reductions that must have landed before
+    the caller continues, a blocking call waits for everything pending -- this is how the G2 bucket and G1's up-conv bucket
+    overlap G1's backward while D's bucket gates `optim_D.step` (src/cgan.py:305)."""
 
     def __init__(self, buffers, process_group=None):
         self.buffers = buffers          # callable name -> tensor (buffers may be allocated lazily)
@@ -71,16 +72,19 @@ class GradientSync:
             self.world = dist.get_world_size(process_group)
         self.log = []                   # (names, blocking) in call order, for tests
 
-    def reduce(self, names, blocking, pending):
+    def reduce(self, names, blocking, pending, wait=()):
         self.log.append((tuple(names), bool(blocking)))
         if self.world > 1:
             import torch.distributed as dist
             for n in names:
-                pending.append(dist.all_reduce(self.buffers(n), op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
-        if blocking:
-            for wk in pending:
+                pending.append((n, dist.all_reduce(self.buffers(n), op=dist.ReduceOp.SUM, group=self.pg, async_op=True)))
+        keep = []
+        for n, wk in pending:
+            if blocking or n in wait:
                 wk.wait()
-            pending.clear()
+            else:
+                keep.append((n, wk))
+        pending[:] = keep
 
 
 @dataclass
@@ -129,7 +133,10 @@ class STCGANEngine:
         self.optim_D.set_packed_grads({**self.rt["D1"].param_grad_views, **self.rt["D2"].param_grad_views})
         self.optim_G.set_pack_targets(self.rt["G1"].convs + self.rt["G2"].convs)
         self.optim_D.set_pack_targets(self.rt["D1"].convs + self.rt["D2"].convs)
-        self.sync = GradientSync(lambda n: self.rt[n].flat_grad, process_group)
+        def bucket(name):                  # "G1" -> whole flat buffer, "G1.ups" / "G1.rest" -> its slices
+            net, _, part = name.partition(".")
+            return self.rt[net].grad_bucket(part or None)
+        self.sync = GradientSync(bucket, process_group)
         self.pg, self.world = process_group, self.sync.world
         self.optim_G.grad_scale = self.optim_D.grad_scale = 1.0 / self.world
         self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
@@ -192,7 +199,8 @@ class STCGANEngine:
             rt["D2"].backward(w2f, d2f, False)
         L.join()
         del w1r, w1f, w2r, w2f
-        yield ("D1", "D2"), True                              # blocking: optim_D needs the reduced gradients
+        if self.world > 1:          # (single GPU: no exchange, the whole step is one CUDA graph)
+            yield ("D1", "D2"), True                          # blocking: optim_D needs the reduced gradients
         self.optim_D.step()                                   # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
@@ -223,19 +231,25 @@ class STCGANEngine:
         ops.unpack_input_grad(di1, 3, 1, dm, True)
         dig2 = rt["G2"].backward(wg2, dy, True)
         ops.unpack_input_grad(dig2, 3, 1, dm, True)           # G2's input gradient, mask channel (cgan.py:286)
-        yield ("G2",), False                                  # async: overlaps G1's backward
-        split = self.world == 1 and bool(L.streams)
+        if self.world > 1:
+            yield ("G2",), False                              # async: overlaps G1's backward
+        # G1's backward in two halves: after the decoder half its up-conv weight gradients (64 % of G1's parameters) are
+        # final and go on the wire under the encoder half; by then G2's sum has landed, so G2's share of optim_G.step
+        # (cgan.py:351; an HBM-bound stream over 28 B/parameter) runs on a lane underneath the encoder half as well
+        rt["G1"].backward(wg1, dm, False, part="dec")
+        if self.world > 1:
+            yield ("G1.ups",), False, ("G2",)
+        split = bool(L.streams)
         if split:
-            # single GPU: G2's gradients are final, so G2's share of optim_G.step (cgan.py:351; an HBM-bound stream over
-            # 28 B/parameter) runs on a lane underneath G1's tensor-bound backward pass
             L.fork()
             with L.lane(0):
                 self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False,
                                           max_ctas=int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148")))
-        rt["G1"].backward(wg1, dm, False)
+        rt["G1"].backward(wg1, dm, False, part="enc")
         if split:
             L.join()
-        yield ("G1",), True
+        if self.world > 1:
+            yield ("G1.rest",), True
         if split:
             self.optim_G.step_partial(list(self.nets["G1"].parameters()), tick=False, last=True)
         else:
@@ -243,8 +257,9 @@ class STCGANEngine:
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step
 
-    def _reduce(self, names, blocking, pending):
-        self.sync.reduce(names, blocking, pending)
+    def _reduce(self, req, pending):
+        names, blocking = req[0], req[1]
+        self.sync.reduce(names, blocking, pending, wait=req[2] if len(req) > 2 else ())
 
     # ------------------------------------------------------------------------------------------
     def train_step(self, x, m, y):
@@ -254,8 +269,8 @@ class STCGANEngine:
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise RuntimeError("train_step expects float32 CUDA tensors")
         pending = []
-        for names, blocking in self._step_segments(x.contiguous(), m.contiguous(), y.contiguous()):
-            self._reduce(names, blocking, pending)
+        for req in self._step_segments(x.contiguous(), m.contiguous(), y.contiguous()):
+            self._reduce(req, pending)
         return self.losses
 
     def capture(self, x, m, y, warmup=3):
@@ -285,7 +300,7 @@ class STCGANEngine:
             self._graphs.append((g, req))
             if req is None:
                 break
-            self._reduce(req[0], req[1], pending)     # keep ranks in lock-step during capture as well
+            self._reduce(req, pending)                # keep ranks in lock-step during capture as well
         self.graph_launches = _lib.launch_count() - before
         self._graph = True
         return self._graphs
@@ -301,7 +316,7 @@ class STCGANEngine:
         for g, req in self._graphs:
             g.replay()
             if req is not None:
-                self._reduce(req[0], req[1], pending)
+                self._reduce(req, pending)
         self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
         return self.losses
 

@@ -289,7 +289,8 @@ class _NetRuntimeBase:
         if self.flat_grad is not None and self.flat_grad.device == self.device():
             return
         sizes = []
-        for c in self.convs:
+        order = getattr(self, "_grad_order", self.convs)     # (a generator puts its up-conv gradients first: bucket "ups")
+        for c in order:
             sizes.append(("w", c, 16 * c.d0 * c.d1))
         for c in self.convs:
             if c.bias is not None:
@@ -320,6 +321,19 @@ class _NetRuntimeBase:
         self.alloc_grads()
         self.flat_grad.zero_()
 
+    def grad_bucket(self, name=None):
+        """Slices of the flat gradient buffer that are all-reduced separately: None / "all" = everything; for a generator
+        "ups" = the up-conv weight gradients (final after the decoder half of backward), "rest" = everything else."""
+        self.alloc_grads()
+        if name in (None, "all"):
+            return self.flat_grad
+        n_ups = getattr(self, "_n_ups", 0)
+        if name == "ups":
+            return self.flat_grad[:n_ups]
+        if name == "rest":
+            return self.flat_grad[n_ups:]
+        raise KeyError(name)
+
     def grads_in_parameter_layout(self, params):
         """torch-layout gradients for autograd (conv weights are un-packed by a kernel)."""
         out = []
@@ -341,6 +355,8 @@ class GeneratorRuntime(_NetRuntimeBase):
         self.cpad = max(4, (in_channels + 3) // 4 * 4)
         convs = list(downs) + list(ups)
         bns = [b for b in down_bns if b is not None] + [b for b in up_bns if b is not None]
+        self._grad_order = list(ups) + list(downs)
+        self._n_ups = sum((16 * c.d0 * c.d1 + 3) // 4 * 4 for c in ups)
         super().__init__(convs, bns, precision)
 
     def sizes(self, h, w):
@@ -414,14 +430,20 @@ class GeneratorRuntime(_NetRuntimeBase):
         ws["out"] = out
         return out, ws
 
-    def backward(self, ws, dout, need_input_grad, param_grads=True):
+    def backward(self, ws, dout, need_input_grad, param_grads=True, part=None):
         """dout: NCHW fp32 gradient of the output.  Accumulates parameter gradients into the flat buffer;
-        returns the NHWC gradient of the packed input (or None)."""
+        returns the NHWC gradient of the packed input (or None).
+        `part`: None = the whole pass; "dec" = the decoder half only (afterwards every up-conv weight gradient -- the
+        "ups" gradient bucket, 64 % of the network's parameters -- is final, so its all-reduce can run under the encoder half);
+        "enc" = the rest (dout is ignored)."""
         dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
         training = ws["training"]
         n = ws["n"]
         C = [None] + [d.cout for d in self.downs]
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+        if part == "enc":
+            dcat = ws.pop("_dcat_last")
+            return self._backward_encoder(ws, dcat, need_input_grad, param_grads)
         ws["arena"].acc.zero_()            # all BatchNorm backward reductions of this pass accumulate into it
         # ---- outermost up conv (+Tanh)
         up = self.ups[0]
@@ -446,6 +468,16 @@ class GeneratorRuntime(_NetRuntimeBase):
                 self._wgrad_async(ws, lambda up=up, x_in=x_in, guy=guy: up.wgrad(x_in, guy), guy)
             dcat_prev, dcat = dcat, up.dgrad(guy, *s[k])
             ws.setdefault("dcat", {})[k - 1] = dcat_prev
+        if part == "dec":
+            ws["_dcat_last"] = dcat
+            self._join_side(ws)
+            return None
+        return self._backward_encoder(ws, dcat, need_input_grad, param_grads)
+
+    def _backward_encoder(self, ws, dcat, need_input_grad, param_grads):
+        dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
+        training, n = ws["training"], ws["n"]
+        C = [None] + [d.cout for d in self.downs]
         dcats = ws["dcat"]
         # ---- encoder, inside-out.  `da` = gradient w.r.t. the activated tensor feeding the next down conv
         da = dcat                       # at k = L: gradient w.r.t. relu(x_L)
