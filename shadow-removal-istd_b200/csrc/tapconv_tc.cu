@@ -957,7 +957,8 @@ static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st
 }
 
 template <int BN, int STAGES>
-static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st) {
+static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st,
+                                     int ctas_per_sm = 1) {
   using SM = PersistSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -966,7 +967,8 @@ static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_
     configured = true;
   }
   const int total = m_tiles * n_tiles * nclass;
-  const int grid = total < 148 ? total : 148;
+  const int cap = 148 * ctas_per_sm;
+  const int grid = total < cap ? total : cap;
   launch_k(tapgemm_tc_persistent_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P, m_tiles, n_tiles, total);
   return finish_launch();
 }
@@ -1278,12 +1280,19 @@ int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, 
   if (rc) return rc;
   if (persistent_mode() != 0) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
-    if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, 1, st);
-    return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, 1, st);
+    // two K steps per tile: these launches are bound by the epilogue (TMEM -> bf16 rows -> global), not by the ring, so
+    // they run several shallow persistent CTAs per SM (3 x 4 epilogue warps for 128x64 tiles) instead of one deep one
+    const char* e = getenv("STCGAN_THINK_DEEP");
+    if (e && e[0] == '1') {
+      if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, 1, st);
+      return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, 1, st);
+    }
+    if (BN == 128) return launch_tapgemm_persistent<128, 2>(P, m_tiles, Nout / BN, 1, st, 2);
+    return launch_tapgemm_persistent<64, 2>(P, m_tiles, Nout / BN, 1, st, 3);
   }
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), 1);
-  if (BN == 128) return launch_tapgemm<128, 3>(P, grid, st);
-  return launch_tapgemm<64, 4>(P, grid, st);
+  if (BN == 128) return launch_tapgemm<128, 2>(P, grid, st);
+  return launch_tapgemm<64, 2>(P, grid, st);
 }
 
 template <int BN, int STAGES>

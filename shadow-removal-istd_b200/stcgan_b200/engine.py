@@ -132,6 +132,13 @@ class STCGANEngine:
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
         self.optim_D.set_packed_grads({**self.rt["D1"].param_grad_views, **self.rt["D2"].param_grad_views})
         self.optim_G.set_pack_targets(self.rt["G1"].convs + self.rt["G2"].convs)
+        # optim_G is applied in three partial launches, one per gradient bucket, in the order the buckets become final:
+        # G2, G1's up-conv weights ("G1.ups"), the rest of G1
+        g2_ids = {id(p) for p in G2.parameters()}
+        ups_ids = {id(c.weight) for c in self.rt["G1"].ups}
+        self._g1_ups = [c.weight for c in self.rt["G1"].ups]
+        self._g1_rest = [p for p in G1.parameters() if id(p) not in ups_ids]
+        self.optim_G.set_block_order(lambda p: 0 if id(p) in g2_ids else (1 if id(p) in ups_ids else 2))
         self.optim_D.set_pack_targets(self.rt["D1"].convs + self.rt["D2"].convs)
         def bucket(name):                  # "G1" -> whole flat buffer, "G1.ups" / "G1.rest" -> its slices
             net, _, part = name.partition(".")
@@ -249,10 +256,15 @@ class STCGANEngine:
         if split:
             L.join()
         if self.world > 1:
-            yield ("G1.rest",), True
+            yield ("G1.rest",), False, ("G1.ups",)            # the last bucket goes on the wire ...
         if split:
-            self.optim_G.step_partial(list(self.nets["G1"].parameters()), tick=False, last=True)
+            self.optim_G.step_partial(self._g1_ups, tick=False, last=False)      # ... under the update of the bucket before it
+            if self.world > 1:
+                yield (), True
+            self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
         else:
+            if self.world > 1:
+                yield (), True
             self.optim_G.step()                               # cgan.py:351
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step

@@ -27,10 +27,17 @@ class FusedAdam(torch.optim.Optimizer):
         self._packed_grads = {}  # id(param) -> (flat fp32 view, d0, d1): engine-provided packed gradients
         self._pack_targets = {}  # id(param) -> ConvOp whose bf16 packed copies the Adam kernel refreshes in the same pass
         self.grad_scale = 1.0
+        self._order_key = None   # optional: parameter -> sort key of its blocks in the device table (see set_block_order)
 
     def set_packed_grads(self, views):
         """Engine hook: gradients that live in packed [16][d0][d1] layout instead of `p.grad`."""
         self._packed_grads = dict(views)
+        self._tables.clear()
+
+    def set_block_order(self, key):
+        """Engine hook: order the tensors of the device table by `key(param)` (stable), so that groups of parameters that
+        are updated by separate `step_partial` calls (one per gradient bucket) occupy contiguous block ranges."""
+        self._order_key = key
         self._tables.clear()
 
     def set_pack_targets(self, convs):
@@ -74,7 +81,10 @@ class FusedAdam(torch.optim.Optimizer):
         chunk = _lib.load().stcgan_adam_chunk()
         tile = _lib.load().stcgan_adam_tile()
         entries, blocks, keep, fused, ranges = [], [], [], [], {}
-        for p in group["params"]:
+        params = list(group["params"])
+        if self._order_key is not None:
+            params.sort(key=self._order_key)
+        for p in params:
             gd = self._grad_of(p)
             if gd is None:
                 continue
