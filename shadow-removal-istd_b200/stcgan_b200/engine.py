@@ -366,3 +366,20 @@ def infer(G1, G2, x, quantize=True):
     if not quantize:
         return mp, yp, None, None
     return mp, yp, ops.float2uint_hwc(mp), ops.float2uint_hwc(yp)
+
+
+@torch.no_grad()
+def infer_u8(G1, G2, x_u8, out_m=None, out_y=None):
+    """CGAN.infer end to end on decoded images: `x_u8` = uint8 [N,H,W,3] as cv2 gives it (host-pinned or device).  The
+    dataset transform (src/dataset.py:100-110,152), G1 -> G2 (cgan.py:437-438) and utils.float2uint (cgan.py:441-446) all run
+    on the GPU; returns (m_u8 [N,H,W,1], y_u8 [N,H,W,3]) on the device, or -- when pinned host buffers `out_m` / `out_y` are
+    given -- copies them there asynchronously (synchronise the stream before reading them)."""
+    dev = next(G1.parameters()).device
+    x8 = x_u8 if x_u8.is_cuda else x_u8.to(dev, non_blocking=True)
+    x = ops.u8_to_nchw(x8)
+    _, _, m8, y8 = infer(G1, G2, x)
+    if out_m is not None:
+        out_m.copy_(m8, non_blocking=True)
+    if out_y is not None:
+        out_y.copy_(y8, non_blocking=True)
+    return m8, y8

@@ -154,3 +154,26 @@ def test_inference_and_quantisation_vs_oracle(cuda, lib, states, mode, golden):
     # and the images agree with the reference's to within one grey level almost everywhere
     diff = np.abs(y8.cpu().numpy()[0].astype(int) - oy8[0].astype(int))
     assert diff.max() <= (1 if mode == "fp32" else 6) and (diff > 0).mean() < (0.02 if mode == "fp32" else 0.6)
+
+
+def test_infer_u8_end_to_end_equals_float_path(cuda, lib, states):
+    """stcgan_b200.infer_u8 (uint8 HWC images in, uint8 HWC images out, pinned host buffers) == the float path fed with the
+    dataset transform of the same images (src/dataset.py:100-110,152)."""
+    import stcgan_b200 as S
+    nets = _build("bf16", cuda, states)
+    nets["G1"].eval(); nets["G2"].eval()
+    g = torch.Generator().manual_seed(11)
+    img = torch.randint(0, 256, (2, 96, 128, 3), generator=g, dtype=torch.uint8)
+    # the reference's host-side transform in numpy float32 (src/utils.py:60-62, src/dataset.py:152)
+    x = torch.from_numpy(np.ascontiguousarray(((img.numpy().astype(np.float32) / 255).transpose(0, 3, 1, 2) - 0.5) * 2))
+    _, _, m8_ref, y8_ref = S.infer(nets["G1"], nets["G2"], x.to(cuda))
+    out_m = torch.empty((2, 96, 128, 1), dtype=torch.uint8).pin_memory()
+    out_y = torch.empty((2, 96, 128, 3), dtype=torch.uint8).pin_memory()
+    m8, y8 = S.infer_u8(nets["G1"], nets["G2"], img.pin_memory(), out_m, out_y)
+    torch.cuda.synchronize()
+    # (the bottleneck layers reduce their split-K partial sums with fp32 atomics in arbitrary order, so two runs of the same
+    # network agree only up to a bf16 ulp, i.e. an occasional grey level)
+    for a, b in ((m8, m8_ref), (y8, y8_ref)):
+        d = (a.int() - b.int()).abs()
+        assert int(d.max()) <= 2 and float((d > 0).float().mean()) < 0.05
+    assert torch.equal(out_m, m8.cpu()) and torch.equal(out_y, y8.cpu())
