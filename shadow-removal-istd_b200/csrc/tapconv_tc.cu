@@ -1015,6 +1015,16 @@ static int bn_select(int Nout) {
   return Nout % 128 == 0 ? 128 : 64;
 }
 
+static int wgrad_split_floor() {  // STCGAN_WGRAD_SPLIT_CEIL=1 restores the old ceil() split count (experiments)
+  const char* e = getenv("STCGAN_WGRAD_SPLIT_CEIL");
+  return !(e && e[0] == '1');
+}
+
+static int bn256_auto() {         // STCGAN_TC_BN256_AUTO=0 disables the wave-aware choice of 128x256 tiles
+  const char* e = getenv("STCGAN_TC_BN256_AUTO");
+  return !(e && e[0] == '0');
+}
+
 static int deep_ring_mode() {     // STCGAN_TC_DEEP=0 disables the 6/8-stage variants for single-wave launches
   static int v = -1;
   if (v < 0) { const char* e = getenv("STCGAN_TC_DEEP"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1120,8 +1130,12 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     for (int p = 0; p < 2; ++p)
       for (int q = 0; q < 2; ++q) {
         const long long vw = (g.IW - q + 1) / 2, vh = (g.IH - p + 1) / 2;   // rows 2a'+p < IH
-        // a view can be empty when IH or IW == 1; keep a valid 1-wide map (never selected inside range)
-        rc = encode_nhwc(&P.amap[p * 2 + q], xb + ((long long)p * g.IW + q) * ldx, K, vw, vh, g.N,
+        // a view can be empty when IH or IW == 1; keep a valid 1-wide map (never selected inside range).  Its base must
+        // still be a mapped address: base + (p*IW + q) pixels can lie past the end of the tensor -- and of the allocation
+        // segment -- and the TMA unit faults on an unmapped tensor-map base even if every coordinate is out of range
+        // (observed: illegal address with a 2 x 1 x 1 x 512 input that ended on a 2 MB segment boundary)
+        const bool empty = vw < 1 || vh < 1;
+        rc = encode_nhwc(&P.amap[p * 2 + q], empty ? xb : xb + ((long long)p * g.IW + q) * ldx, K, vw, vh, g.N,
                          2LL * ldx, 2LL * g.IW * ldx, sn, P.wt, P.ht, P.nt);
         if (rc) return rc;
       }
@@ -1129,6 +1143,14 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   // deep-K layers with few output tiles (the U-Net bottleneck) split their taps over extra CTAs and reduce in fp32; that
   // path keeps 128-wide tiles (its fp32 staging tile must fit the pipeline smem)
   int BNsel = bn_select(Nout);
+  // wave-aware tile width: when 128-wide tiles need more than one wave of 2 x 148 resident CTAs and 256-wide tiles (2 stages,
+  // still two CTAs per SM) fit into one with most SMs doubly occupied, the wider tile wins (measured: D's c4 forward
+  // 62 -> 52 us, d3's input gradient 36.5 -> 30.4 us); with fewer CTAs the starved 2-stage ring loses (c4 dgrad 58 -> 81 us)
+  if (BNsel == 128 && Nout % 256 == 0 && !thin_n && bn256_auto()) {
+    const long long m_tiles_ = (long long)P.tiles_w * P.tiles_h * tiles_n * g.nclass;
+    const long long c128 = m_tiles_ * (Nout / 128), c256 = m_tiles_ * (Nout / 256);
+    if (c128 > 296 && c256 <= 296 && c256 >= 200) BNsel = 256;
+  }
   int ksplit = 1;
   if (!thin_n && Nout % 64 == 0) {
     const int bn_s = Nout % 128 == 0 ? 128 : 64;
@@ -1195,7 +1217,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);
   }
   dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)g.nclass);
-  if (BN == 256) return bn256_stages() == 4 ? launch_tapgemm<256, 4>(P, grid, st) : launch_tapgemm<256, 2>(P, grid, st);
+  if (BN == 256) return (bn_select(Nout) == 256 && bn256_stages() == 4) ? launch_tapgemm<256, 4>(P, grid, st) : launch_tapgemm<256, 2>(P, grid, st);
   // launches that leave at most one CTA per SM get a deeper ring instead of a second resident CTA: with 3 stages a lone CTA
   // covers only ~96 KB of the ~170 KB that must be in flight to feed the tensor pipe (measured 0.40 us per 128x128x64 step
   // against 0.21 us with two resident CTAs)
@@ -1319,7 +1341,8 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
   const int BN = D1 % 128 == 0 ? 128 : 64;
   const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
   const int out_tiles = (D0 / 128) * (D1 / BN) * 16;
-  int splits = (2 * 148 + out_tiles - 1) / out_tiles;      // aim for ~2 CTAs per SM
+  // one wave: at most 2 x 148 resident CTAs (a 297th CTA would run alone in a second wave and double the launch time)
+  int splits = wgrad_split_floor() ? (2 * 148) / out_tiles : (2 * 148 + out_tiles - 1) / out_tiles;
   if (splits > total_tiles) splits = total_tiles;
   if (splits < 1) splits = 1;
   P.tiles_per_split = (total_tiles + splits - 1) / splits;
@@ -1338,8 +1361,9 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
   } else {
     for (int p = 0; p < 2; ++p)
       for (int q = 0; q < 2; ++q) {
-        rc = encode_nhwc_blk(&P.lmap[p * 2 + q], lb + ((long long)p * LW + q) * ldl, D1, (LW - q + 1) / 2, (LH - p + 1) / 2, N,
-                             2LL * ldl, 2LL * LW * ldl, sn, P.wt, P.ht, P.nt, BN / 64);
+        const bool empty = (LW - q + 1) / 2 < 1 || (LH - p + 1) / 2 < 1;     // see tapconv_tc: keep the base mapped
+        rc = encode_nhwc_blk(&P.lmap[p * 2 + q], empty ? lb : lb + ((long long)p * LW + q) * ldl, D1, (LW - q + 1) / 2,
+                             (LH - p + 1) / 2, N, 2LL * ldl, 2LL * LW * ldl, sn, P.wt, P.ht, P.nt, BN / 64);
         if (rc) return rc;
       }
   }
@@ -1375,7 +1399,7 @@ int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const 
   const int BN = Dfat % 128 == 0 ? 128 : 64;
   const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
   const int out_tiles = Dfat / BN;
-  int splits = (2 * 148 + out_tiles - 1) / out_tiles;
+  int splits = wgrad_split_floor() ? (2 * 148) / out_tiles : (2 * 148 + out_tiles - 1) / out_tiles;
   if (splits > total_tiles) splits = total_tiles;
   if (splits < 1) splits = 1;
   P.tiles_per_split = (total_tiles + splits - 1) / splits;

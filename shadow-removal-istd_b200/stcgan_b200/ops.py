@@ -14,6 +14,9 @@ from . import _lib
 from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, BACKEND_FFMA, BACKEND_TC, BF16, F32,
                    GEOM_PARITY, GEOM_WIN_S1, GEOM_WIN_S1_FLIP, GEOM_WIN_S2, LossTerm, check)
 
+import os as _os
+_TRACE = bool(_os.environ.get("STCGAN_TRACE"))
+
 DTYPES = {"fp32": (F32, torch.float32), "bf16": (BF16, torch.bfloat16)}
 
 
@@ -82,6 +85,11 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
         _, _, _, _, ldy = _nhwc(out)
         y, nchw = out, 0
     ws, ws_bytes = None, 0
+    if _TRACE:
+        import sys
+        print(f"[stcgan trace] tapconv geom={geom} x={tuple(x.shape)} ldx={ldx} -> ({oh},{ow},{nout}) ldy={ldy} backend={backend} "
+              f"bias={bias is not None} act={act} bn_acc={bn_acc is not None} x_ptr={x.data_ptr():#x} y_ptr={y.data_ptr():#x}",
+              file=sys.stderr, flush=True)
     if backend == BACKEND_TC and n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
         wst = torch.empty(n * oh * ow * nout, dtype=torch.float32, device=x.device)     # split-K partial sums
         ws, ws_bytes = wst.data_ptr(), wst.numel() * 4
