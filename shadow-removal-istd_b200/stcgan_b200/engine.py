@@ -48,12 +48,24 @@ class _Lanes:
 
     def lane_wait(self, i):
         if self.streams:
-            self.streams[i].wait_stream(torch.cuda.current_stream())
+            self.streams[i % len(self.streams)].wait_stream(torch.cuda.current_stream())
 
     def join(self):
         cur = torch.cuda.current_stream()
         for s in self.streams:
             cur.wait_stream(s)
+
+    def record(self, i):
+        """event after everything issued so far on lane i (None when the lanes are disabled: program order suffices)"""
+        if not self.streams:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.streams[i % len(self.streams)])
+        return ev
+
+    def wait_event(self, i, ev):
+        if self.streams and ev is not None:
+            self.streams[i % len(self.streams)].wait_event(ev)
 
 
 class GradientSync:
@@ -164,47 +176,45 @@ class STCGANEngine:
         L = self.lanes
         rt["D1"].zero_grads(); rt["D2"].zero_grads()
         # every distinct input concatenation (cgan.py:281-289, 321-324) is packed once per step and shared.
-        # lane 0: D1 real -> D1 fake, lane 1: D2 real -> D2 fake, main stream: G1 -> G2 (each D keeps its two passes in the
-        # reference order on one stream: the BatchNorm running statistics are order-dependent)
+        # Each of the four discriminator passes is an independent chain  forward -> its loss term -> backward  (the terms
+        # of D_loss are separable, and the backward passes only meet in atomic accumulations), so every pass runs on its
+        # own lane and starts the moment its inputs exist: the two `real` passes at once, D1's `fake` pass after G1's
+        # forward, D2's after G2's -- all of it underneath the generator chain on the main stream.  The only ordering kept
+        # between the two passes of one discriminator is forward-after-forward: the BatchNorm running statistics are
+        # order-dependent (real first, as in the reference).
+        self.losses.zero_()
         L.fork()
+
+        def d_pass(net, sources, packed, target, lam, slot):
+            c, w = rt[net].forward(sources, True, packed=packed)
+            after_fwd = L.record({"D1": 0, "D2": 1}[net]) if target == real else None
+            d = newg(c)
+            ops.fused_loss([dict(kind=kind, a=c, grad=d, target=target, weight=0.5 * lam, loss_weight=0.5, slot=slot)],
+                           self.losses)
+            rt[net].backward(w, d, False)
+            return c, w, d, after_fwd
+
         with L.lane(0):
             pk_xm = rt["D1"].pack_sources([x, m])
-            c1r, w1r = rt["D1"].forward([x, m], True, packed=pk_xm)
+            c1r, w1r, d1r, ev1 = d_pass("D1", [x, m], pk_xm, real, cfg.lambda2, 0)
         with L.lane(1):
             pk_xmy = rt["D2"].pack_sources([x, m, y])
-            c2r, w2r = rt["D2"].forward([x, m, y], True, packed=pk_xmy)
+            c2r, w2r, d2r, ev2 = d_pass("D2", [x, m, y], pk_xmy, real, cfg.lambda3, 1)
         mp, wg1 = rt["G1"].forward([x], True)
         pk_xmp = rt["D1"].pack_sources([x, mp])
-        L.lane_wait(0)
-        with L.lane(0):
-            c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)
+        L.lane_wait(2)
+        L.wait_event(2, ev1)
+        with L.lane(2):
+            c1f, w1f, d1f, _ = d_pass("D1", [x, mp], pk_xmp, fake, cfg.lambda2, 0)
         share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
         yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
         pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
-        L.lane_wait(1)
-        with L.lane(1):
-            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)
+        L.lane_wait(3)
+        L.wait_event(3, ev2)
+        with L.lane(3):
+            c2f, w2f, d2f, _ = d_pass("D2", [x, mp, yp], pk_xmpyp, fake, cfg.lambda3, 1)
         L.join()
         self.last = dict(m_pred=mp, y_pred=yp)
-        self.losses.zero_()
-        d1r, d1f, d2r, d2f = newg(c1r), newg(c1f), newg(c2r), newg(c2f)
-        ops.fused_loss([
-            dict(kind=kind, a=c1r, grad=d1r, target=real, weight=0.5 * cfg.lambda2, loss_weight=0.5, slot=0),
-            dict(kind=kind, a=c1f, grad=d1f, target=fake, weight=0.5 * cfg.lambda2, loss_weight=0.5, slot=0),
-            dict(kind=kind, a=c2r, grad=d2r, target=real, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
-            dict(kind=kind, a=c2f, grad=d2f, target=fake, weight=0.5 * cfg.lambda3, loss_weight=0.5, slot=1),
-        ], self.losses)
-        L.fork()
-        # the four backward passes only meet in atomic accumulations (packed weight gradients, BatchNorm / bias gradients)
-        with L.lane(0):
-            rt["D1"].backward(w1r, d1r, False)
-        with L.lane(1):
-            rt["D2"].backward(w2r, d2r, False)
-        with L.lane(2):
-            rt["D1"].backward(w1f, d1f, False)
-        with L.lane(3):
-            rt["D2"].backward(w2f, d2f, False)
-        L.join()
         del w1r, w1f, w2r, w2f
         if self.world > 1:          # (single GPU: no exchange, the whole step is one CUDA graph)
             yield ("D1", "D2"), True                          # blocking: optim_D needs the reduced gradients
