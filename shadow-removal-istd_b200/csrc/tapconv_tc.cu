@@ -66,24 +66,28 @@ __device__ __forceinline__ long long gtime() {
 }
 #define DBG_T(slot) do { if (P.dbg) P.dbg[(((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); } while (0)
 
-template <int BN, int STAGES>
+// MT = number of 128-row accumulators per CTA (M tile = MT x 128 pixels): MT = 2 halves the CTA count of launches that
+// would need more than one wave, shares every weight tile between two MMAs and amortises the issuing thread's per-stage
+// wait + commit (~250 cycles, profiles/r01_pipeline_microbenchmarks.txt) over 8 MMAs instead of 4
+template <int BN, int STAGES, int MT = 1>
 struct TapGemmSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  static constexpr int A_BYTES = MT * TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
   // epilogue reuse of the (idle) pipeline smem: bf16 staging tile, then the column-statistics scratch
-  static constexpr int STAT_OFFSET = (TC_BM * (BN * 2 + 16) + 127) / 128 * 128;
+  static constexpr int STAT_OFFSET = (MT * TC_BM * (BN * 2 + 16) + 127) / 128 * 128;
   static_assert(BN < 64 || STAT_OFFSET + 2 * 1024 * 4 <= BAR_OFFSET, "statistics scratch must fit in the pipeline smem");
+  static_assert(MT == 1 || (BN >= 64 && MT * BN <= 512), "two accumulators need 2 x BN TMEM columns");
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 __global__ void __launch_bounds__(192)
 tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   pdl_trigger();
-  using SM = TapGemmSmem<BN, STAGES>;
+  using SM = TapGemmSmem<BN, STAGES, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
@@ -192,11 +196,13 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
-          }
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + mt * (TC_BM * TC_BK * 2) + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (it | k) != 0);
+            }
         }
         umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
       }
@@ -207,11 +213,11 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   } else if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> bias/activation -> bf16 NHWC =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;          // accumulator row = grid pixel inside the tile
-    const int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
-    const int a = a0 + hl, b = b0 + wl, n = n0 + nl;
-    const int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
-    const bool valid = n < P.N && oy < P.OH && ox < P.OW;
+    int row = q * 32 + lane;                // accumulator row = grid pixel inside the tile (first accumulator)
+    int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
+    int a = a0 + hl, b = b0 + wl, n = n0 + nl;
+    int oy = a * P.ostride + P.oy0[cls], ox = b * P.ostride + P.ox0[cls];
+    bool valid = n < P.N && oy < P.OH && ox < P.OW;
     __nv_bfloat16* out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
     mbar_wait_warp(tmem_full, 0, lane);
     if (threadIdx.x == 64) DBG_T(4);
@@ -241,46 +247,57 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     } else if (P.part_out == nullptr) {
       // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced
       constexpr int PITCH = BN * 2 + 16;
-      const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
       const float slope = act_slope(P.act);
       const float* bias = P.bias;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-            if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
-            f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            w[e] = valid ? *reinterpret_cast<const uint32_t*>(&h) : 0u;     // rows outside the tensor count as zeros below
-          }
-          st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt > 0) {                           // rows 128.. of the tile live in the second accumulator
+          row = mt * TC_BM + q * 32 + lane;
+          wl = row % P.wt; hl = (row / P.wt) % P.ht; nl = row / (P.wt * P.ht);
+          a = a0 + hl; b = b0 + wl; n = n0 + nl;
+          oy = a * P.ostride + P.oy0[cls]; ox = b * P.ostride + P.ox0[cls];
+          valid = n < P.N && oy < P.OH && ox < P.OW;
+          out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
         }
-      }
-      __syncwarp();
-      if (threadIdx.x == 64) DBG_T(7);
-      constexpr int LPR = BN * 2 / 16;     // lanes per output row (16-byte pieces)
-      constexpr int RPI = 32 / LPR;        // rows per warp-wide store instruction
-      const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
-      const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32) * PITCH;
+        const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0), r);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+              if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+              f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              w[e] = valid ? *reinterpret_cast<const uint32_t*>(&h) : 0u;     // rows outside the tensor count as zeros below
+            }
+            st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
+          }
+        }
+        __syncwarp();
+        if (threadIdx.x == 64) DBG_T(7);
+        constexpr int LPR = BN * 2 / 16;     // lanes per output row (16-byte pieces)
+        constexpr int RPI = 32 / LPR;        // rows per warp-wide store instruction
+        const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+        const uint32_t wbase = smem_u32(smem) + (uint32_t)(mt * TC_BM + q * 32) * PITCH;
 #pragma unroll 4
-      for (int i = 0; i < 32; i += RPI) {
-        const int rr = i + lane / LPR;
-        const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
-        if (pr) {
-          const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16);
-          *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+        for (int i = 0; i < 32; i += RPI) {
+          const int rr = i + lane / LPR;
+          const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+          if (pr) {
+            const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16);
+            *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+          }
         }
       }
       if (P.bn_acc) {
         // BatchNorm statistics of this tile from the staged bf16 values: thread (rg, cg) sums 8 channels over its row
         // group, the row groups are combined through smem, one fp64 atomic pair per channel and CTA
-        constexpr int CG = BN / 8, RG = 128 / CG, RPG = 128 / RG;
+        constexpr int CG = BN / 8, RG = 128 / CG, RPG = MT * TC_BM / RG;
         asm volatile("bar.sync 1, 128;" ::: "memory");              // all four epilogue warps have staged their rows
         const int et = threadIdx.x - 64, cg = et % CG, rg = et / CG;
         float s8[8], q8[8];
@@ -293,9 +310,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
           const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float a = __uint_as_float(w4[i] << 16), b = __uint_as_float(w4[i] & 0xffff0000u);
-            s8[2 * i] += a; q8[2 * i] = fmaf(a, a, q8[2 * i]);
-            s8[2 * i + 1] += b; q8[2 * i + 1] = fmaf(b, b, q8[2 * i + 1]);
+            const float fa = __uint_as_float(w4[i] << 16), fb = __uint_as_float(w4[i] & 0xffff0000u);
+            s8[2 * i] += fa; q8[2 * i] = fmaf(fa, fa, q8[2 * i]);
+            s8[2 * i + 1] += fb; q8[2 * i + 1] = fmaf(fb, fb, q8[2 * i + 1]);
           }
         }
         float* red = reinterpret_cast<float*>(smem + SM::STAT_OFFSET);      // [2][RG][BN]
@@ -935,24 +952,24 @@ static int dump_debug_times(const TapGemmParams& P0, dim3 grid, cudaStream_t st,
   return rc;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st);
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
-  return dump_debug_times(P, grid, st, BN, &launch_tapgemm_raw<BN, STAGES>);
+  return dump_debug_times(P, grid, st, BN, &launch_tapgemm_raw<BN, STAGES, MT>);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
-  using SM = TapGemmSmem<BN, STAGES>;
+  using SM = TapGemmSmem<BN, STAGES, MT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  launch_k(tapgemm_tc_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P);
+  launch_k(tapgemm_tc_kernel<BN, STAGES, MT>, grid, 192, SM::TOTAL, st, P);
   return finish_launch();
 }
 
@@ -1018,6 +1035,11 @@ static int bn_select(int Nout) {
 static int wgrad_split_floor() {  // STCGAN_WGRAD_SPLIT_CEIL=1 restores the old ceil() split count (experiments)
   const char* e = getenv("STCGAN_WGRAD_SPLIT_CEIL");
   return !(e && e[0] == '1');
+}
+
+static int mt_mode() {            // STCGAN_TC_MT: unset = automatic, 1 = one accumulator per CTA always, 2 = two whenever possible
+  const char* e = getenv("STCGAN_TC_MT");
+  return !e ? 0 : (e[0] == '2' ? 2 : 1);
 }
 
 static int bn256_auto() {         // STCGAN_TC_BN256_AUTO=0 disables the wave-aware choice of 128x256 tiles
@@ -1114,6 +1136,24 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   if (GH <= 0 || GW <= 0) return 0;
   choose_tile(TC_BM, GW, GH, g.N, &P.wt, &P.ht, &P.nt);
   P.tiles_w = (GW + P.wt - 1) / P.wt; P.tiles_h = (GH + P.ht - 1) / P.ht;
+  // M tile of 2 x 128 pixels (two accumulators per CTA) for launches that would otherwise need more than one wave of
+  // resident CTAs: half the CTAs, every weight tile feeds two MMAs, the per-stage wait + commit is paid once per 8 MMAs
+  int MTsel = 1;
+  if (!thin_n && Nout % 64 == 0) {
+    const int bn1 = Nout % 128 == 0 ? 128 : 64;
+    const long long ctas1 = (long long)P.tiles_w * P.tiles_h * ((g.N + P.nt - 1) / P.nt) * (Nout / bn1) * g.nclass;
+    const int mode = mt_mode();
+    // measured (tools/conv_probe.py, us per launch, one vs two accumulators): e2 fwd 23.5 -> 21.4, c3 dgrad 23.4 -> 21.7,
+    // d3 fwd 35.8 -> 34.3; 128x64 tiles lose (c2 dgrad 34.6 -> 40.4, d2 fwd 54.7 -> 61.2: they live on residency, 3-4 CTAs
+    // per SM), and where 128x256 tiles bring the launch into one wave those win instead (c4 fwd 51.1 vs 59.1)
+    const long long c256 = Nout % 256 == 0 ? ctas1 / 2 : 0;
+    const bool wide_wins = bn256_auto() && c256 >= 200 && c256 <= 296;
+    if ((mode == 2 && ctas1 > 148) || (mode == 0 && bn1 == 128 && ctas1 > 296 && !wide_wins)) MTsel = 2;
+  }
+  if (MTsel == 2) {
+    choose_tile(2 * TC_BM, GW, GH, g.N, &P.wt, &P.ht, &P.nt);
+    P.tiles_w = (GW + P.wt - 1) / P.wt; P.tiles_h = (GH + P.ht - 1) / P.ht;
+  }
   const int tiles_n = (g.N + P.nt - 1) / P.nt;
   P.GH = GH; P.GW = GW; P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.ostride = g.ostride;
   P.ntaps = g.ntaps; P.kchunks = K / 64;
@@ -1143,10 +1183,11 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   // deep-K layers with few output tiles (the U-Net bottleneck) split their taps over extra CTAs and reduce in fp32; that
   // path keeps 128-wide tiles (its fp32 staging tile must fit the pipeline smem)
   int BNsel = bn_select(Nout);
+  if (MTsel == 2 && BNsel == 256) BNsel = 128;
   // wave-aware tile width: when 128-wide tiles need more than one wave of 2 x 148 resident CTAs and 256-wide tiles (2 stages,
   // still two CTAs per SM) fit into one with most SMs doubly occupied, the wider tile wins (measured: D's c4 forward
   // 62 -> 52 us, d3's input gradient 36.5 -> 30.4 us); with fewer CTAs the starved 2-stage ring loses (c4 dgrad 58 -> 81 us)
-  if (BNsel == 128 && Nout % 256 == 0 && !thin_n && bn256_auto()) {
+  if (BNsel == 128 && Nout % 256 == 0 && !thin_n && bn256_auto() && MTsel == 1) {
     const long long m_tiles_ = (long long)P.tiles_w * P.tiles_h * tiles_n * g.nclass;
     const long long c128 = m_tiles_ * (Nout / 128), c256 = m_tiles_ * (Nout / 256);
     if (c128 > 296 && c256 <= 296 && c256 >= 200) BNsel = 256;
@@ -1156,7 +1197,7 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     const int bn_s = Nout % 128 == 0 ? 128 : 64;
     const long long ctas_s = (long long)P.tiles_w * P.tiles_h * tiles_n * (Nout / bn_s) * g.nclass;
     const long long need_s = (long long)g.N * g.OH * g.OW * Nout * 4;
-    if (ws && ws_bytes >= need_s && ctas_s <= 74 && g.ntaps * P.kchunks >= 32) {
+    if (ws && ws_bytes >= need_s && ctas_s <= 74 && g.ntaps * P.kchunks >= 32 && MTsel == 1) {
       while (ksplit * 2 <= g.ntaps && ctas_s * ksplit * 2 <= 296) ksplit *= 2;
       if (ksplit > 1) BNsel = bn_s;
     }
@@ -1206,6 +1247,11 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     P.bn_acc = nullptr;     // (the GEMM launch above already ran; statistics come from the finished sums)
     launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy, bn_acc);
     return finish_launch();
+  }
+  if (MTsel == 2) {
+    if (BNsel == 256) BNsel = 128;
+    dim3 grid2((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BNsel), (unsigned)g.nclass);
+    return BNsel == 128 ? launch_tapgemm<128, 2, 2>(P, grid2, st) : launch_tapgemm<64, 2, 2>(P, grid2, st);
   }
   if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;

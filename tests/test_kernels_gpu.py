@@ -183,6 +183,38 @@ def test_conv_epilogue_batchnorm_statistics(cuda, lib, case):
     assert rel_err(_nchw(o3), F.relu(bn(_nchw(y).double()))) < 6e-3
 
 
+MT2_CASES = [
+    ("conv2", 64, 128, 6, 128, 128),    # 192 tiles of 128 pixels -> 96 CTAs with two accumulators each
+    ("convT", 128, 128, 6, 31, 33),     # four parity classes, odd grid, ragged 256-pixel tiles
+    ("conv1", 128, 256, 8, 40, 40),     # stride 1, two N tiles
+]
+
+
+@pytest.mark.parametrize("case", MT2_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_two_accumulator_tiles(cuda, lib, case, monkeypatch):
+    """M tiles of 2 x 128 pixels (two TMEM accumulators per CTA, STCGAN_TC_MT=2 forces the path the library picks on its own
+    for multi-wave launches): forward + fused BatchNorm statistics against torch, and == the one-accumulator kernel."""
+    from stcgan_b200 import _lib, ops
+    kind, cin, cout, n, h, w_ = case
+    op, w, _ = _convop(kind, cin, cout, "bf16", cuda)
+    g = torch.Generator().manual_seed(7)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), "bf16")
+    ref = _ref_forward(kind, x.double(), _round(w, "bf16").double(), None)
+    oh, ow = ref.shape[2:]
+    xk = _nhwc(x, torch.bfloat16, cuda)
+    monkeypatch.setenv("STCGAN_TC_MT", "1")
+    y1 = op.forward(xk, oh, ow)
+    monkeypatch.setenv("STCGAN_TC_MT", "2")
+    acc = torch.zeros((_lib.BN_SLOTS, 2, cout), dtype=torch.float64, device=cuda)
+    y2 = op.forward(xk, oh, ow, bn_acc=acc)
+    torch.cuda.synchronize()
+    assert rel_err(_nchw(y2), ref) < TOL["bf16"]
+    assert torch.equal(y1, y2), "same MMAs in the same order: bit-identical to the one-accumulator kernel"
+    yd = y2.double().cpu().reshape(-1, cout)
+    tot = acc.sum(dim=0).cpu()
+    assert rel_err(tot[0], yd.sum(0)) < 1e-5 and rel_err(tot[1], (yd * yd).sum(0)) < 1e-5
+
+
 def test_pack_weight_layout(cuda, lib):
     from stcgan_b200 import ops
     w = torch.randn(24, 40, 4, 4)

@@ -18,6 +18,8 @@ SHAPES = [  # geom, N, IH, IW, K, OH, OW, Nout, name
     (3, 16, 64, 64, 256, 128, 128, 64, "d2 fwd N=64 16 it"),
     (3, 16, 16, 16, 1024, 32, 32, 256, "d4 fwd parity N=256 64 it"),
     (0, 16, 64, 64, 128, 32, 32, 512, "d3 dgrad N=512 32 it"),
+    (3, 16, 32, 32, 256, 64, 64, 128, "c3 dgrad parity N=128 16 it"),
+    (3, 16, 32, 32, 512, 64, 64, 128, "d3 fwd parity N=128 32 it"),
 ]
 
 
@@ -47,8 +49,8 @@ def run(shape, reps=20):
     return us, fl / us / 1e6
 
 
-KEYS = ("STCGAN_TC_DBGMODE", "STCGAN_TC_STAGES", "STCGAN_TC_BN256", "STCGAN_TC_BN256_STAGES")
-envs = [{}, dict(STCGAN_TC_DBGMODE="4"), dict(STCGAN_TC_DBGMODE="5"), dict(STCGAN_TC_BN256="1", STCGAN_TC_DBGMODE="4")]
+KEYS = ("STCGAN_TC_DBGMODE", "STCGAN_TC_STAGES", "STCGAN_TC_BN256", "STCGAN_TC_BN256_STAGES", "STCGAN_TC_MT", "STCGAN_TC_BN256_AUTO")
+envs = [{}, dict(STCGAN_TC_MT="1", STCGAN_TC_BN256_AUTO="0"), dict(STCGAN_TC_MT="2"), dict(STCGAN_TC_MT="1")]
 print(f"{'shape':34s} " + " ".join(f"{','.join(k[10:] + '=' + v for k, v in e.items()) or 'default':>16s}" for e in envs) + "   (us, TF/s-equivalent)")
 for sh in SHAPES:
     cells = []
