@@ -480,12 +480,21 @@ adam_kernel(const stcgan_adam_tensor* __restrict__ table, const int32_t* __restr
     const int tiles1 = t.d1 / ADAM_TILE;
     const int td0 = (chunk / tiles1) * ADAM_TILE, td1 = (chunk % tiles1) * ADAM_TILE;
     // phase 1: gradient tile, 128-byte rows per (tap, d0)
-#pragma unroll 4
-    for (int i = threadIdx.x; i < 16 * ADAM_TILE * (ADAM_TILE / 4); i += 256) {
-      const int tap = i / (ADAM_TILE * 8), r0 = (i / 8) % ADAM_TILE, c4 = (i % 8) * 4;
-      const float4 g = ldg_stream4(t.g + (long long)tap * plane + (long long)(td0 + r0) * t.d1 + td1 + c4);
-      float* d = g_s + (r0 * ADAM_TILE + c4) * ADAM_G_PITCH + tap;
-      d[0] = g.x; d[ADAM_G_PITCH] = g.y; d[2 * ADAM_G_PITCH] = g.z; d[3 * ADAM_G_PITCH] = g.w;
+    {
+      float4 gr[16];          // all 16 loads of this thread in flight before the first shared-memory store
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = u * 256 + threadIdx.x;
+        const int tap = i / (ADAM_TILE * 8), r0 = (i / 8) % ADAM_TILE, c4 = (i % 8) * 4;
+        gr[u] = ldg_stream4(t.g + (long long)tap * plane + (long long)(td0 + r0) * t.d1 + td1 + c4);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = u * 256 + threadIdx.x;
+        const int tap = i / (ADAM_TILE * 8), r0 = (i / 8) % ADAM_TILE, c4 = (i % 8) * 4;
+        float* d = g_s + (r0 * ADAM_TILE + c4) * ADAM_G_PITCH + tap;
+        d[0] = gr[u].x; d[ADAM_G_PITCH] = gr[u].y; d[2 * ADAM_G_PITCH] = gr[u].z; d[3 * ADAM_G_PITCH] = gr[u].w;
+      }
     }
     __syncthreads();
     // phase 2: 32 rows of 32 pairs x 16 parameters = 128 float4 per row; 2 rows per pass, 4 passes in flight

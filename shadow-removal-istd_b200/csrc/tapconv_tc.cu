@@ -858,18 +858,29 @@ tapwgrad_tc_kernel(const __grid_constant__ WgradParams P) {
     mbar_wait_warp(tmem_full, 0, lane);
     tc_fence_after();
     if (P.thin) {
-      const int wtap = P.flip ? 15 - row / 8 : row / 8, c = row % 8;
+      // stage the fp32 tile [(tap, c)][d] in (now idle) pipeline smem, then accumulate with consecutive threads on
+      // consecutive addresses of G: for one tap the (d, c) block -- or the (c, d) rows -- of this CTA is contiguous
+      // (scalar atomics issued row-per-thread hit 32 different cache lines per instruction and serialised the 296 CTAs)
+      constexpr int PITCH = BN + 1;
+      float* stage = reinterpret_cast<float*>(smem);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if (c < P.thin_c) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int d = d1_0 + c0 + e;
-            const long long idx = P.fat_is_dim0 ? ((long long)wtap * P.Dfat + d) * P.thin_c + c
-                                                : ((long long)wtap * P.thin_c + c) * P.Dfat + d;
-            atomicAdd(P.G + idx, __uint_as_float(r[e]));
+        for (int e = 0; e < 32; ++e) stage[row * PITCH + c0 + e] = __uint_as_float(r[e]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64, tc = P.thin_c, per_tap = BN * tc;
+      for (int t = 0; t < 16; ++t) {
+        const int wtap = P.flip ? 15 - t : t;
+        for (int j = et; j < per_tap; j += 128) {
+          if (P.fat_is_dim0) {           // G[wtap][d][c]: j = d_local * thin_c + c
+            const int dl = j / tc, c = j - dl * tc;
+            atomicAdd(P.G + ((long long)wtap * P.Dfat + d1_0) * tc + j, stage[(t * 8 + c) * PITCH + dl]);
+          } else {                       // G[wtap][c][d]: j = c * BN + d_local
+            const int c = j / BN, dl = j - c * BN;
+            atomicAdd(P.G + ((long long)wtap * tc + c) * P.Dfat + d1_0 + dl, stage[(t * 8 + c) * PITCH + dl]);
           }
         }
       }
