@@ -342,6 +342,56 @@ class STCGANEngine:
         self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
         return self.losses
 
+    def replay_async(self, x, m, y):
+        """Pipelined form of `replay` for a training loop that feeds host batches: the pinned host tensors x, m, y are copied
+        into a double-buffered device inbox on a copy stream (the transfer of batch i+1 runs underneath the compute of
+        batch i), the captured step first moves its inbox into the graph's static inputs, and the step's losses are copied
+        to pinned host memory behind it.  Returns the losses of the PREVIOUS call as a host tensor (None on the first call)
+        -- the only host synchronisation is on a step that has had a whole step's time to finish; `flush()` returns the
+        last one."""
+        if not self._graph:
+            raise RuntimeError("call capture() first")
+        if getattr(self, "_pipe", None) is None:
+            mk = lambda: tuple(torch.empty_like(t) for t in self._static)
+            self._pipe = dict(i=0, inbox=[mk(), mk()], copy=torch.cuda.Stream(device=self.device),
+                              loss=[torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)],
+                              ready=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
+                              done=[torch.cuda.Event() for _ in range(2)], primed=[False, False])
+        P = self._pipe
+        i = P["i"]
+        main = torch.cuda.current_stream()
+        if P["primed"][i]:
+            P["copy"].wait_event(P["consumed"][i])        # the step that last used this inbox slot has copied it out
+        with torch.cuda.stream(P["copy"]):
+            for dst, src in zip(P["inbox"][i], (x, m, y)):
+                dst.copy_(src, non_blocking=True)
+            P["ready"][i].record(P["copy"])
+        main.wait_event(P["ready"][i])
+        for dst, src in zip(self._static, P["inbox"][i]):
+            dst.copy_(src, non_blocking=True)
+        P["consumed"][i].record(main)
+        self.replay()
+        P["loss"][i].copy_(self.losses, non_blocking=True)
+        P["done"][i].record(main)
+        P["primed"][i] = True
+        P["i"] = 1 - i
+        j = 1 - i
+        if not P["primed"][j]:
+            return None
+        P["done"][j].synchronize()
+        return P["loss"][j].clone()
+
+    def flush(self):
+        """Host copy of the losses of the last `replay_async` call (waits for that step)."""
+        P = getattr(self, "_pipe", None)
+        if P is None:
+            return None
+        j = 1 - P["i"]
+        if not P["primed"][j]:
+            return None
+        P["done"][j].synchronize()
+        return P["loss"][j].clone()
+
     def replay_u8(self, x8, m8, y8):
         """Captured step fed with decoded uint8 HWC images ([B,H,W,3], [B,H,W,1], [B,H,W,3]; host-pinned or device): the
         dataset's uint8 -> [-1,1] float CHW transform (src/dataset.py:100-110,152) runs on the GPU."""

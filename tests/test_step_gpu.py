@@ -177,3 +177,23 @@ def test_infer_u8_end_to_end_equals_float_path(cuda, lib, states):
         d = (a.int() - b.int()).abs()
         assert int(d.max()) <= 2 and float((d > 0).float().mean()) < 0.05
     assert torch.equal(out_m, m8.cpu()) and torch.equal(out_y, y8.cpu())
+
+
+def test_replay_async_pipelines_inputs_and_loss_reads(cuda, lib, states):
+    """STCGANEngine.replay_async: host batches in through the double-buffered inbox, losses out one step later; the values
+    are those of the plain replay path (same captured graph, same inputs)."""
+    import stcgan_b200 as S
+    nets = _build("bf16", cuda, states)
+    eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"])
+    batches = [tuple(t.contiguous().pin_memory() for t in O.make_istd_batch(2, 64, 64, seed=s)) for s in (1, 2, 3)]
+    eng.capture(*(t.to(cuda) for t in batches[0]), warmup=1)
+    assert eng.replay_async(*batches[0]) is None
+    l0 = eng.replay_async(*batches[1])                   # losses of the step on batches[0]
+    l1 = eng.replay_async(*batches[2])
+    l2 = eng.flush()
+    torch.cuda.synchronize()
+    for l in (l0, l1, l2):
+        assert l is not None and not l.is_cuda and torch.isfinite(l).all()
+    assert torch.equal(l2, eng.losses.cpu())             # the last step's losses are what the device holds
+    assert not torch.equal(l0, l1) and not torch.equal(l1, l2)
+    assert float(eng.optim_G.state_dict()["state"][0]["step"]) == 5     # 1 warm-up + capture + 3 replays
