@@ -152,8 +152,8 @@ def instrumented_breakdown(eng, x, m, y):
     # the instrumented step runs every kernel on ONE stream (the production step forks the weight-gradient kernels onto a
     # side stream, where per-launch event intervals on the main stream would not bracket them)
     side = {k: rt.side_stream for k, rt in eng.rt.items()}
-    lanes = eng.lanes.streams
-    eng.lanes.streams = []
+    lanes, hi = eng.lanes.streams, eng.hi_stream
+    eng.lanes.streams, eng.hi_stream = [], None
     for rt in eng.rt.values():
         rt.side_stream = None
     try:
@@ -169,7 +169,7 @@ def instrumented_breakdown(eng, x, m, y):
             setattr(ops, name, fn)
         for k, rt in eng.rt.items():
             rt.side_stream = side[k]
-        eng.lanes.streams = lanes
+        eng.lanes.streams, eng.hi_stream = lanes, hi
     fam = {}
     for name, fl, e0, e1 in rec:
         t, f, c = fam.get(name, (0.0, 0.0, 0))

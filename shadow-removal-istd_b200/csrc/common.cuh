@@ -35,12 +35,23 @@ template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const int on = pdl_enabled();
-  cfg.attrs = on ? attr : nullptr;
-  cfg.numAttrs = on ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  // a kernel launched on a high-priority stream carries that priority as a launch attribute, so that it survives CUDA-graph
+  // capture (captured kernel nodes do not inherit the priority of the stream they were captured on)
+  int prio = 0;
+  if (cudaStreamGetPriority(st, &prio) == cudaSuccess && prio != 0) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = prio;
+    ++na;
+  }
+  cfg.attrs = na ? attr : nullptr;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through finish_launch()
 }
 

@@ -139,6 +139,11 @@ class STCGANEngine:
         for k, r in self.rt.items():
             r.side_stream = self.side_streams["G" if k in ("G1", "G2") else k]
         self.lanes = _Lanes([mk(), mk(), mk(), mk()] if conc else [])
+        # opt-in (STCGAN_HI_PRIORITY=1): the generator chain -- the step's critical path -- on a HIGH-priority stream.
+        # Measured on B200: helps the eager step (6.65 -> 6.42 ms: G1's forward 1.37 -> 0.69 ms) but not the captured
+        # graph (6.13 -> 6.25 ms, with the priority carried as a kernel launch attribute), so it is off by default
+        hi = conc and os.environ.get("STCGAN_HI_PRIORITY", "0") == "1"
+        self.hi_stream = torch.cuda.Stream(device=self.device, priority=-1) if hi else None
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
@@ -162,6 +167,22 @@ class STCGANEngine:
         self._graph = None
         self._static = None
         self.last = {}
+
+    def _critical(self):
+        """Context: issue on the high-priority stream (forked from / joined into the current stream)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            if self.hi_stream is None:
+                yield
+                return
+            cur = torch.cuda.current_stream()
+            self.hi_stream.wait_stream(cur)
+            with torch.cuda.stream(self.hi_stream):
+                yield
+            cur.wait_stream(self.hi_stream)
+        return ctx()
 
     # ------------------------------------------------------------------------------------------
     def _step_segments(self, x, m, y):
@@ -200,19 +221,20 @@ class STCGANEngine:
         with L.lane(1):
             pk_xmy = rt["D2"].pack_sources([x, m, y])
             c2r, w2r, d2r, ev2 = d_pass("D2", [x, m, y], pk_xmy, real, cfg.lambda3, 1)
-        mp, wg1 = rt["G1"].forward([x], True)
-        pk_xmp = rt["D1"].pack_sources([x, mp])
-        L.lane_wait(2)
-        L.wait_event(2, ev1)
-        with L.lane(2):
-            c1f, w1f, d1f, _ = d_pass("D1", [x, mp], pk_xmp, fake, cfg.lambda2, 0)
-        share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
-        yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
-        pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
-        L.lane_wait(3)
-        L.wait_event(3, ev2)
-        with L.lane(3):
-            c2f, w2f, d2f, _ = d_pass("D2", [x, mp, yp], pk_xmpyp, fake, cfg.lambda3, 1)
+        with self._critical():
+            mp, wg1 = rt["G1"].forward([x], True)
+            pk_xmp = rt["D1"].pack_sources([x, mp])
+            L.lane_wait(2)
+            L.wait_event(2, ev1)
+            with L.lane(2):
+                c1f, w1f, d1f, _ = d_pass("D1", [x, mp], pk_xmp, fake, cfg.lambda2, 0)
+            share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
+            yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
+            pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
+            L.lane_wait(3)
+            L.wait_event(3, ev2)
+            with L.lane(3):
+                c2f, w2f, d2f, _ = d_pass("D2", [x, mp, yp], pk_xmpyp, fake, cfg.lambda3, 1)
         L.join()
         self.last = dict(m_pred=mp, y_pred=yp)
         del w1r, w1f, w2r, w2f
@@ -246,14 +268,16 @@ class STCGANEngine:
         ops.unpack_input_grad(di2, 3, 1, dm, True)
         L.join()
         ops.unpack_input_grad(di1, 3, 1, dm, True)
-        dig2 = rt["G2"].backward(wg2, dy, True)
-        ops.unpack_input_grad(dig2, 3, 1, dm, True)           # G2's input gradient, mask channel (cgan.py:286)
+        with self._critical():
+            dig2 = rt["G2"].backward(wg2, dy, True)
+            ops.unpack_input_grad(dig2, 3, 1, dm, True)       # G2's input gradient, mask channel (cgan.py:286)
         if self.world > 1:
             yield ("G2",), False                              # async: overlaps G1's backward
         # G1's backward in two halves: after the decoder half its up-conv weight gradients (64 % of G1's parameters) are
         # final and go on the wire under the encoder half; by then G2's sum has landed, so G2's share of optim_G.step
         # (cgan.py:351; an HBM-bound stream over 28 B/parameter) runs on a lane underneath the encoder half as well
-        rt["G1"].backward(wg1, dm, False, part="dec")
+        with self._critical():
+            rt["G1"].backward(wg1, dm, False, part="dec")
         if self.world > 1:
             yield ("G1.ups",), False, ("G2",)
         split = bool(L.streams)
@@ -262,7 +286,8 @@ class STCGANEngine:
             with L.lane(0):
                 self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False,
                                           max_ctas=int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148")))
-        rt["G1"].backward(wg1, dm, False, part="enc")
+        with self._critical():
+            rt["G1"].backward(wg1, dm, False, part="enc")
         if split:
             L.join()
         if self.world > 1:

@@ -21,6 +21,7 @@ eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"])
 for rt in eng.rt.values():
     rt.side_stream = None          # per-launch event intervals need every kernel on the timing stream
 eng.lanes.streams = []
+eng.hi_stream = None
 x, m, y = (t.contiguous().to(dev) for t in O.make_istd_batch(batch, H, W))
 for _ in range(3):
     eng.train_step(x, m, y)
