@@ -127,7 +127,19 @@ def instrumented_breakdown(eng, x, m, y):
     def thinwgrad_flops(t, stride, thin_c, f, g, *a, **k):
         return 2.0 * f.shape[0] * f.shape[1] * f.shape[2] * f.shape[3] * 128
 
+    def bn_apply_bytes(yy, *a, **k):
+        out1, out2 = a[11], (a[13] if len(a) > 13 else k.get("out2"))
+        return float(yy.numel() * 2 + out1.numel() * 2 + (0 if out2 is None else out2.numel() * 2))
+
+    def bn_bwd_bytes(yy, ss, mi, gamma, training, g1, act1, g2, act2, acc, dy, *a, **k):
+        e = dy.numel() * 2
+        g2b = 0 if g2 is None else e
+        return float((2 * e + g2b) * (2 if ss is not None else 1) + e)     # reduce pass + apply pass (+ dy)
+
+    big = lambda yy, *a, **k: "hbm_big" if yy.numel() * 2 >= 16 * 2 ** 20 else "hbm_small"
     table = {
+        "bn_fused_apply": (bn_apply_bytes, lambda *a, **k: "bn_fwd_" + big(*a, **k)),
+        "bn_act_bwd": (bn_bwd_bytes, lambda *a, **k: "bn_bwd_" + big(*a, **k)),
         "tapconv": (conv_flops, lambda *a, **k: "conv_tc" if k.get("backend") == BACKEND_TC else "conv_ffma"),
         "tapwgrad": (wgrad_flops, lambda *a, **k: "wgrad_tc" if k.get("backend") == BACKEND_TC else "wgrad_ffma"),
         "tapconv_thin_n": (conv_flops, lambda *a, **k: "conv_tc_thin"),
@@ -149,6 +161,17 @@ def instrumented_breakdown(eng, x, m, y):
     for name, (ff, nf) in table.items():
         saved[name] = getattr(ops, name)
         setattr(ops, name, timed(saved[name], ff, nf))
+    # optimiser launches: 28 B per parameter (p, m, v read + written, g read) + 4 B of refreshed bf16 copies
+    adam_saved = []
+    for opt in (eng.optim_D, eng.optim_G):
+        for meth in ("step", "step_partial"):
+            fn = getattr(opt, meth)
+            adam_saved.append((opt, meth, fn))
+            if meth == "step":
+                nb = lambda *a, _o=opt, **k: 32.0 * sum(p.numel() for g in _o.param_groups for p in g["params"])
+            else:
+                nb = lambda params, *a, **k: 32.0 * sum(p.numel() for p in params)
+            setattr(opt, meth, timed(fn, nb, lambda *a, **k: "adam"))
     # the instrumented step runs every kernel on ONE stream (the production step forks the weight-gradient kernels onto a
     # side stream, where per-launch event intervals on the main stream would not bracket them)
     side = {k: rt.side_stream for k, rt in eng.rt.items()}
@@ -167,6 +190,8 @@ def instrumented_breakdown(eng, x, m, y):
     finally:
         for name, fn in saved.items():
             setattr(ops, name, fn)
+        for opt, meth, fn in adam_saved:
+            setattr(opt, meth, fn)
         for k, rt in eng.rt.items():
             rt.side_stream = side[k]
         eng.lanes.streams, eng.hi_stream = lanes, hi
@@ -289,8 +314,20 @@ def run_b200(args, rank, world, local_rank):
             "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all full-width tcgen05 conv launches of one train step)",
             "eager_step_seconds": eager_s,
             "launches": tc_n, "flops_per_step": tc_f, "seconds_per_step": tc_t, "peak_source": peaks["source"] + ", sustained bf16",
-            "families": {k: {"s": v[0], "flops": v[1], "launches": v[2]} for k, v in fam.items()},
+            "families": {k: {"s": v[0], "flops": v[1], "launches": v[2]} for k, v in fam.items()
+                         if k.startswith(("conv_", "wgrad_"))},
             "whole_step_tflops": flops_step / (dt / args.steps) / 1e12}
+    # HBM-bound families of the same instrumented step (algorithmic bytes / CUDA-event time; "big" = tensors >= 16 MB,
+    # i.e. launches long enough for the rate to mean something -- the small ones are latency-bound and L2-resident)
+    hb = {k: v for k, v in fam.items() if k.startswith(("bn_", "adam"))}
+    sel = [v for k, v in hb.items() if k.endswith("_big") or k == "adam"]
+    hbm_t, hbm_b = sum(v[0] for v in sel), sum(v[1] for v in sel)
+    roof_hbm = {"bound": "hbm", "achieved": hbm_b / hbm_t / 1e9 if hbm_t > 0 else 0.0, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": (hbm_b / hbm_t / 1e9 / peaks["hbm"]) if hbm_t > 0 else 0.0, "traffic": None,
+                "kernel": "bn_fused_apply + bn_bwd_reduce/apply on tensors >= 16 MB, adam_kernel (one train step)",
+                "peak_source": peaks["source"],
+                "families": {k: {"s": v[0], "bytes": v[1], "launches": v[2], "GBps": v[1] / v[0] / 1e9 if v[0] > 0 else 0.0}
+                             for k, v in hb.items()}}
     cpu_rate, cores = cpu_oracle_rate(2, 2) if world == 1 else (None, None)
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -312,7 +349,7 @@ def run_b200(args, rank, world, local_rank):
                    "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": 1e3 * dt_u8 / args.steps,
                    "note": "host ships decoded uint8 HWC images; uint8 -> [-1,1] float CHW on the GPU (bit-exact with the dataset code)"},
         "gpu_launches": int(launches_per_step * args.steps),
-        "clocks": clocks, "roofline": roof,
+        "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
         "losses_last_step": dict(zip(S.engine.SLOTS, [float(v) for v in loss_host[:6]])),
     }
     if cpu_rate is not None:

@@ -90,6 +90,8 @@ void stcgan_launch_count_reset(void);
  * also how the reference's odd-size F.pad (stcgan_g.py:126-132) is realised without a copy.
  * workspace (optional, fp32, >= N*OH*OW*Nout*4 bytes): lets the tensor-core backend split the taps of deep-K layers with
  * few output tiles (the U-Net bottleneck) over more CTAs; partial sums are reduced there in fp32.
+ * workspace_bytes < 0: the workspace (|workspace_bytes| bytes) is all zeros on entry and is left all zeros on exit (the
+ * finishing kernel clears what it reads), which saves the memset launch in front of every such convolution.
  */
 int stcgan_tapconv(int geom, int dtype, int backend,
                    const void* x, int N, int IH, int IW, int K, int ldx,

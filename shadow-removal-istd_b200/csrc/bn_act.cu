@@ -248,6 +248,7 @@ bn_act_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const
 struct BnFinalize {
   const double* acc;      // [STCGAN_BN_SLOTS][2][C] (training)
   long long count;        // values per channel
+  double inv_count, unbias;   // 1 / count, count / (count - 1)
   const float* gamma; const float* beta;
   float* rmean; float* rvar;
   float momentum, eps;
@@ -262,19 +263,23 @@ bn_fused_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, con
                       T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
   extern __shared__ float ssm[];     // [2][C]: scale, shift
   pdl_prologue();
+  const double inv_count = f.inv_count, unbias = f.unbias;      // formed on the host
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, invstd;
     if (f.training) {
       double s = 0.0, q = 0.0;
 #pragma unroll
       for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { s += f.acc[(2 * k) * C + c]; q += f.acc[(2 * k + 1) * C + c]; }
-      const double m = s / (double)f.count;
-      double var = q / (double)f.count - m * m;
+      // (fp64 only where cancellation needs it: sums, mean, E[y^2] - mean^2; B200's fp64 divide / sqrt are emulated and
+      // cost microseconds in these latency-bound launches, so 1/count is formed once per thread and invstd in fp32, which
+      // is also what torch's float kernels compute)
+      const double m = s * inv_count;
+      double var = q * inv_count - m * m;
       if (var < 0.0) var = 0.0;
       mean = (float)m;
-      invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+      invstd = 1.f / sqrtf((float)(var + (double)f.eps));
       if (blockIdx.x == 0 && f.rmean) {
-        const double unbiased = f.count > 1 ? var * (double)f.count / (double)(f.count - 1) : var;
+        const double unbiased = var * unbias;
         f.rmean[c] = (1.f - f.momentum) * f.rmean[c] + f.momentum * (float)m;
         f.rvar[c] = (1.f - f.momentum) * f.rvar[c] + f.momentum * (float)unbiased;
       }
@@ -435,12 +440,12 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
                     int training, int HC, int WC,
                     const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
                     const double* __restrict__ acc, T* __restrict__ dy, int lddy,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int cv, int rows) {
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, int cv, int rows,
+                    double invP) {
   extern __shared__ float coef[];     // [5][C]: sc, sh, kA, kB, kC   (+ [rows][cv*8] bias-gradient scratch behind it)
   pdl_prologue();
   const bool has_bn = ss != nullptr;
   const bool two = g2 != nullptr;
-  const double invP = 1.0 / (double)P;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float sc = 1.f, sh = 0.f, kA = 1.f, kB = 0.f, kC = 0.f;
     if (has_bn) {
@@ -590,6 +595,8 @@ int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy
   if (PC == 0) return 0;
   const RowMap m = row_map(C);
   BnFinalize f;
+  f.inv_count = count > 0 ? 1.0 / (double)count : 0.0;
+  f.unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
   f.acc = acc; f.count = count; f.gamma = gamma; f.beta = beta; f.rmean = rmean; f.rvar = rvar;
   f.momentum = momentum; f.eps = eps; f.training = training; f.mean_invstd = mean_invstd; f.scale_shift = scale_shift;
   const size_t smem = (size_t)2 * C * sizeof(float);
@@ -637,12 +644,13 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
   if (dtype == STCGAN_F32)
     launch_k(bn_bwd_apply_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<float>, smem), 256, smem, st,
              static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
-             act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows);
+             act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows,
+             1.0 / (double)P);
   else
     launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
              static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
              static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
-             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows);
+             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows, 1.0 / (double)P);
   return finish_launch();
 }
 

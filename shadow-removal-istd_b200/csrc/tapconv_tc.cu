@@ -1079,8 +1079,8 @@ static int persistent_mode() {
 // (NCHW fp32, bias + any activation) or, if y32 == NULL, to the first 8 channels of an NHWC bf16 tensor.
 // fp32 split-K partial sums [P][Nout] -> bf16 y (pitch ldy) with bias + activation
 __global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
-                     __nv_bfloat16* __restrict__ y, int ldy, double* __restrict__ bn_acc) {
+splitk_finish_kernel(float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
+                     __nv_bfloat16* __restrict__ y, int ldy, double* __restrict__ bn_acc, int clear) {
   pdl_prologue();
   const int quads = Nout / 4;
   const float slope = act_slope(act);
@@ -1089,6 +1089,7 @@ splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, cons
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const long long p = i / quads; const int c = (int)(i % quads) * 4;
       const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
+      if (clear) *reinterpret_cast<float4*>(part + p * Nout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
@@ -1104,6 +1105,7 @@ splitk_finish_kernel(const float* __restrict__ part, long long P, int Nout, cons
   float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long p = (long long)blockIdx.x * rpb + rr; p < P; p += (long long)gridDim.x * rpb) {
     const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
+    if (clear) *reinterpret_cast<float4*>(part + p * Nout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
@@ -1123,6 +1125,10 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
                void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr,
                float* ws = nullptr, long long ws_bytes = 0, double* bn_acc = nullptr) {
   if (bn_acc && (thin_n || act != STCGAN_ACT_NONE || Nout % 64 != 0)) return STCGAN_EUNSUPPORTED;
+  // ws_bytes < 0: the workspace (|ws_bytes| bytes) is all zeros on entry and is left all zeros on exit (the finisher clears
+  // what it reads): a persistent workspace saves the memset launch in front of every split-K convolution
+  const bool ws_clean = ws_bytes < 0;
+  if (ws_clean) ws_bytes = -ws_bytes;
   if (K % 64 != 0 || ldx % 8 != 0 || !al16(x) || !al16(wp)) return STCGAN_EUNSUPPORTED;
   if (!thin_n) {
     if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(y)) return STCGAN_EUNSUPPORTED;
@@ -1241,8 +1247,10 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   // deep-K layers with few output tiles (the U-Net bottleneck): split the taps over extra CTAs, reduce in fp32
   const long long need = (long long)g.N * g.OH * g.OW * Nout * 4;
   if (ksplit > 1) {
-    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
-    if (e != cudaSuccess) return (int)e;
+    if (!ws_clean) {
+      cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)need, st);
+      if (e != cudaSuccess) return (int)e;
+    }
     P.ksplit = ksplit; P.part_out = ws; P.part_ld = Nout; P.bn_acc = nullptr;
     dim3 grid((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BN), (unsigned)(g.nclass * ksplit));
     rc = BN == 256 ? launch_tapgemm<256, 2>(P, grid, st) : BN == 128 ? launch_tapgemm<128, 3>(P, grid, st) : launch_tapgemm<64, 4>(P, grid, st);
@@ -1256,7 +1264,8 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
       blocks = (Ppix + rpb * 4 - 1) / (rpb * 4); if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
     }
     P.bn_acc = nullptr;     // (the GEMM launch above already ran; statistics come from the finished sums)
-    launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy, bn_acc);
+    launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy, bn_acc,
+             ws_clean ? 1 : 0);
     return finish_launch();
   }
   if (MTsel == 2) {

@@ -144,6 +144,9 @@ class STCGANEngine:
         # graph (6.13 -> 6.25 ms, with the priority carried as a kernel launch attribute), so it is off by default
         hi = conc and os.environ.get("STCGAN_HI_PRIORITY", "0") == "1"
         self.hi_stream = torch.cuda.Stream(device=self.device, priority=-1) if hi else None
+        for st in list(self.side_streams.values()) + self.lanes.streams + [self.hi_stream]:
+            if st is not None:
+                ops.register_concurrent_stream(st)
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})

@@ -58,6 +58,15 @@ def _nhwc(t: torch.Tensor):
 
 
 SPLITK_MAX_ELEMS = 4 * 1024 * 1024     # only small outputs (bottleneck layers) get a split-K workspace
+_SPLITK_WS = {}                        # (elements, device, lane) -> zeroed fp32 workspace (kept zero by the finisher)
+_CONCURRENT_STREAMS = set()            # raw handles of streams that run next to the caller's main stream (engine lanes)
+
+
+def register_concurrent_stream(stream):
+    """Tell the library that `stream` runs concurrently with other streams of the same step: work issued on it gets its own
+    persistent scratch (everything else -- the default stream, a warm-up stream, a capture stream -- shares the "main" one,
+    since those never run at the same time)."""
+    _CONCURRENT_STREAMS.add(stream.cuda_stream)
 
 
 def tc_eligible_conv(k: int, nout: int) -> bool:
@@ -91,8 +100,14 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
               f"bias={bias is not None} act={act} bn_acc={bn_acc is not None} x_ptr={x.data_ptr():#x} y_ptr={y.data_ptr():#x}",
               file=sys.stderr, flush=True)
     if backend == BACKEND_TC and n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
-        wst = torch.empty(n * oh * ow * nout, dtype=torch.float32, device=x.device)     # split-K partial sums
-        ws, ws_bytes = wst.data_ptr(), wst.numel() * 4
+        # split-K partial sums: one persistent, self-cleaning (all-zero between calls) workspace per size and stream --
+        # no allocation and no memset launch per convolution; concurrent streams never share one
+        cur = torch.cuda.current_stream().cuda_stream
+        key = (n * oh * ow * nout, x.device.index, cur if cur in _CONCURRENT_STREAMS else 0)
+        wst = _SPLITK_WS.get(key)
+        if wst is None:
+            wst = _SPLITK_WS[key] = torch.zeros(key[0], dtype=torch.float32, device=x.device)
+        ws, ws_bytes = wst.data_ptr(), -wst.numel() * 4
     if bn_acc is not None:
         assert backend == BACKEND_TC and bias is None and act == ACT_NONE and not nchw
         assert bn_acc.dtype == torch.float64 and bn_acc.is_contiguous() and bn_acc.numel() == _lib.BN_SLOTS * 2 * nout
