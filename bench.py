@@ -442,6 +442,7 @@ def main():
     run_b200(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
