@@ -250,6 +250,12 @@ typedef struct stcgan_loss_term {
 } stcgan_loss_term;
 int stcgan_fused_loss(const stcgan_loss_term* host_terms, int nterms, float* loss_out, void* stream);
 
+/* relativistic logits of AdversarialLoss (src/loss.py:88-96, 102-110) on [N, M] float tensors (M = elements per sample):
+ *   backward == 0: out[n,i] = a[n,i] - b[n,i]  (avg == 0, RpGAN)  or  a[n,i] - mean over the batch of b[.,i]  (avg != 0, RaGAN)
+ *   backward != 0: the gradient of that map w.r.t. b for an upstream gradient passed as `b`: out = -b  or  -mean over the batch
+ *                  of b[.,i] broadcast to every n (a is ignored) */
+int stcgan_rel_logits(const float* a, const float* b, int N, int64_t M, int avg, int backward, float* out, void* stream);
+
 /* ---- optimiser --------------------------------------------------------------------------------------
  * replaces torch.optim.Adam(betas, eps=1e-8, no weight decay, no amsgrad) of src/cgan.py:85-90,305,351 as one
  * multi-tensor launch.  Gradients may be in packed [16][d0][d1] layout (d0 > 0) or torch layout (d0 == 0).

@@ -62,6 +62,7 @@ int nchw_to_nhwc(int dtype, const float* x, int N, int H, int W, int C, void* ou
 int out_act_bwd(int dtype, int act, const float* o, const float* d, int N, int H, int W, int C, int border, void* g, int ldg,
                 cudaStream_t st);
 int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaStream_t st);
+int rel_logits(const float* a, const float* b, int N, long long M, int avg, int backward, float* out, cudaStream_t st);
 int adam_step(const stcgan_adam_tensor* table, const int32_t* blocks, int nblocks, float* hyper, cudaStream_t st);
 int adam_step_range(const stcgan_adam_tensor* table, const int32_t* blocks, int first_block, int nblocks, float* hyper, int tick,
                     int max_ctas, cudaStream_t st);
@@ -277,6 +278,11 @@ int stcgan_out_act_bwd(int dtype, int act, const float* out_nchw, const float* d
 int stcgan_fused_loss(const stcgan_loss_term* host_terms, int nterms, float* loss_out, void* stream) {
   STCGAN_REQUIRE(host_terms && loss_out);
   return fused_loss(host_terms, nterms, loss_out, as_stream(stream));
+}
+
+int stcgan_rel_logits(const float* a, const float* b, int N, int64_t M, int avg, int backward, float* out, void* stream) {
+  STCGAN_REQUIRE(b && out && (a || backward) && N >= 0 && M >= 0);
+  return rel_logits(a, b, N, (long long)M, avg, backward, out, as_stream(stream));
 }
 
 int stcgan_adam_step(const stcgan_adam_tensor* dev_table, const int32_t* dev_blocks, int nblocks,

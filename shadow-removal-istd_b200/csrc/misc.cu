@@ -435,6 +435,35 @@ int fused_loss(const stcgan_loss_term* terms, int nterms, float* loss_out, cudaS
 }
 
 // ---------------------------------------------------------------------------------------------
+// relativistic logits (src/loss.py:88-96, 102-110): out[n,i] = a[n,i] - b[n,i]               (RpGAN)
+//                                                   out[n,i] = a[n,i] - mean_n' b[n',i]      (RaGAN: batch mean, dim 0)
+// and the gradient w.r.t. b of the same map: db[n,i] = -g[n,i]  /  -(1/N) sum_n' g[n',i]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rel_logits_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, long long M, int avg, int backward,
+                  float* __restrict__ out) {
+  pdl_prologue();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    float mb = 0.f;
+    if (avg) {
+      for (int n = 0; n < N; ++n) mb += b[(long long)n * M + i];
+      mb = mb / (float)N;
+    }
+    for (int n = 0; n < N; ++n) {
+      const long long k = (long long)n * M + i;
+      out[k] = backward ? -(avg ? mb : b[k]) : a[k] - (avg ? mb : b[k]);
+    }
+  }
+}
+
+int rel_logits(const float* a, const float* b, int N, long long M, int avg, int backward, float* out, cudaStream_t st) {
+  if (N <= 0 || M <= 0) return 0;
+  long long blocks = (M + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(rel_logits_kernel, (unsigned)blocks, 256, 0, st, a, b, N, M, avg, backward, out);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
 // multi-tensor Adam (torch.optim.Adam semantics: eps added after sqrt(v_hat); no weight decay / amsgrad)
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 // ---------------------------------------------------------------------------------------------

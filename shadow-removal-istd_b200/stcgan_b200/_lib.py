@@ -73,6 +73,7 @@ SIGNATURES = {
     "stcgan_nchw_to_nhwc": (_i, [_i, _p, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_out_act_bwd": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p]),
     "stcgan_fused_loss": (_i, [C.POINTER(LossTerm), _i, _p, _p]),
+    "stcgan_rel_logits": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p]),
     "stcgan_adam_step": (_i, [_p, _p, _i, _p, _p]),
     "stcgan_adam_step_range": (_i, [_p, _p, _i, _i, _p, _i, _i, _p]),
     "stcgan_adam_chunk": (_i, []),

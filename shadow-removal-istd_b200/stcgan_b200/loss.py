@@ -36,6 +36,24 @@ class _FusedTermFn(torch.autograd.Function):
         return None, g, None, None, None
 
 
+class _RelLogitsFn(torch.autograd.Function):
+    """a - b (RpGAN) or a - b.mean(dim=0) (RaGAN) as one kernel, with its gradient (src/loss.py:88-96, 102-110)."""
+
+    @staticmethod
+    def forward(ctx, a, b, avg):
+        if not a.is_cuda:
+            raise RuntimeError("stcgan_b200 losses run on CUDA only (no CPU fallback)")
+        ctx.avg = avg
+        return ops.rel_logits(a.detach().contiguous().float(), b.detach().contiguous().float(), avg)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        ga = g if ctx.needs_input_grad[0] else None
+        gb = ops.rel_logits(None, g, ctx.avg, backward=True) if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
 class DataLoss(nn.Module):
     """L1 between prediction and target (src/loss.py:14-26)."""
     __slots__ = ["reduction", "norm"]
@@ -73,14 +91,14 @@ class AdversarialLoss(nn.Module):
         real, fake = self._labels
         if D_loss:
             if self.rel:
-                if self.avg:   # RaGAN (loss.py:90-94); the batch means are tiny torch reductions
-                    return (self.cal_loss(C_real - C_fake.mean(dim=0), real)
-                            + self.cal_loss(C_fake - C_real.mean(dim=0), fake)) * 0.5
-                return self.cal_loss(C_real - C_fake, real)                      # RpGAN (loss.py:96)
+                if self.avg:   # RaGAN (loss.py:90-94): logits relative to the batch mean of the other side
+                    return (self.cal_loss(_RelLogitsFn.apply(C_real, C_fake, True), real)
+                            + self.cal_loss(_RelLogitsFn.apply(C_fake, C_real, True), fake)) * 0.5
+                return self.cal_loss(_RelLogitsFn.apply(C_real, C_fake, False), real)    # RpGAN (loss.py:96)
             return (self.cal_loss(C_real, real) + self.cal_loss(C_fake, fake)) * 0.5   # SGAN (loss.py:98-100)
         if self.rel:
             if self.avg:
-                return (self.cal_loss(C_fake - C_real.mean(dim=0), real)
-                        + self.cal_loss(C_real - C_fake.mean(dim=0), fake)) * 0.5
-            return self.cal_loss(C_fake - C_real, real)
+                return (self.cal_loss(_RelLogitsFn.apply(C_fake, C_real, True), real)
+                        + self.cal_loss(_RelLogitsFn.apply(C_real, C_fake, True), fake)) * 0.5
+            return self.cal_loss(_RelLogitsFn.apply(C_fake, C_real, False), real)
         return self.cal_loss(C_fake, real)                                      # SGAN (loss.py:112)

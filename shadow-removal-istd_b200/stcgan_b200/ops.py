@@ -378,6 +378,20 @@ def fused_loss(terms, loss_out):
     check(_lib.load().stcgan_fused_loss(arr, len(terms), loss_out.data_ptr(), _stream()), "stcgan_fused_loss")
 
 
+def rel_logits(a, b, avg, backward=False):
+    """relativistic logits a - b (RpGAN) / a - mean_batch(b) (RaGAN), or with backward=True the gradient of that map
+    w.r.t. b for the upstream gradient passed as `b` (a ignored)."""
+    _need_cuda(b)
+    assert b.dtype == torch.float32 and b.is_contiguous() and (backward or (a.dtype == torch.float32 and a.is_contiguous()
+                                                                                and a.shape == b.shape))
+    n = b.shape[0]
+    mm = b.numel() // max(n, 1)
+    out = torch.empty_like(b)
+    check(_lib.load().stcgan_rel_logits(None if backward else a.data_ptr(), b.data_ptr(), n, mm, int(avg), int(backward),
+                                        out.data_ptr(), _stream()), "stcgan_rel_logits")
+    return out
+
+
 def float2uint_hwc(x_nchw):
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     n, c, h, w = x_nchw.shape
