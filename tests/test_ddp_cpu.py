@@ -46,6 +46,17 @@ def _worker(rank, world, port, out_dir):
     sync.reduce(("G1",), True, pending)
     assert not pending and torch.equal(bufs["G2"], torch.arange(4.0) * 3) and torch.equal(bufs["G1"], torch.ones(2) * 3)
     assert sync.log == [(("D1", "D2"), True), (("G2",), False), (("G1",), True)] and sync.world == 2
+    # bucketed schedule of the engine's G phase: G2 async, then G1's up-conv bucket async while G2 must have landed,
+    # then the rest async while the up-conv bucket must have landed, then a blocking wait for everything
+    bufs.update({"G2": torch.ones(4) * (rank + 1), "G1.ups": torch.ones(3) * (rank + 1), "G1.rest": torch.ones(2) * (rank + 1)})
+    pending = []
+    sync.reduce(("G2",), False, pending)
+    sync.reduce(("G1.ups",), False, pending, wait=("G2",))
+    assert [n for n, _ in pending] == ["G1.ups"] and torch.equal(bufs["G2"], torch.ones(4) * 3)
+    sync.reduce(("G1.rest",), False, pending, wait=("G1.ups",))
+    assert [n for n, _ in pending] == ["G1.rest"] and torch.equal(bufs["G1.ups"], torch.ones(3) * 3)
+    sync.reduce((), True, pending)
+    assert not pending and torch.equal(bufs["G1.rest"], torch.ones(2) * 3)
 
     # ---- 2. rank-local BN + summed gradients / world == per-shard forwards averaged
     torch.manual_seed(123)
