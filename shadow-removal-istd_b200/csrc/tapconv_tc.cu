@@ -69,25 +69,30 @@ __device__ __forceinline__ long long gtime() {
 // MT = number of 128-row accumulators per CTA (M tile = MT x 128 pixels): MT = 2 halves the CTA count of launches that
 // would need more than one wave, shares every weight tile between two MMAs and amortises the issuing thread's per-stage
 // wait + commit (~250 cycles, profiles/r01_pipeline_microbenchmarks.txt) over 8 MMAs instead of 4
-template <int BN, int STAGES, int MT = 1>
+// NI = number of MMA issuer threads (1, or 2 = a second issuer in a seventh warp).  The issuers alternate ring stages and
+// accumulate into SEPARATE TMEM accumulators that the epilogue adds up, so no ordering between their MMAs is needed: while
+// one issuer sits in its wait + commit (~250 cycles per stage, not hidden behind the 1-2 MMAs the pipe queues) the other
+// one's MMAs keep the tensor pipe busy (tools/mma_pipe.cu: 524 -> 277 cycles per 128x128x64 stage from one CTA)
+template <int BN, int STAGES, int MT = 1, int NI = 1>
 struct TapGemmSmem {
   static constexpr int A_BYTES = MT * TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
-  static constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
+  static constexpr int TMEM_COLS = NI * MT * BN < 32 ? 32 : NI * MT * BN;
+  static_assert(NI == 1 || (BN >= 64 && NI * MT * BN <= 512 && STAGES >= 2), "two issuers need 2 x MT x BN TMEM columns");
   // epilogue reuse of the (idle) pipeline smem: bf16 staging tile, then the column-statistics scratch
   static constexpr int STAT_OFFSET = (MT * TC_BM * (BN * 2 + 16) + 127) / 128 * 128;
   static_assert(BN < 64 || STAT_OFFSET + 2 * 1024 * 4 <= BAR_OFFSET, "statistics scratch must fit in the pipeline smem");
   static_assert(MT == 1 || (BN >= 64 && MT * BN <= 512), "two accumulators need 2 x BN TMEM columns");
 };
 
-template <int BN, int STAGES, int MT = 1>
-__global__ void __launch_bounds__(192)
+template <int BN, int STAGES, int MT = 1, int NI = 1>
+__global__ void __launch_bounds__(NI == 2 ? 224 : 192)
 tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   pdl_trigger();
-  using SM = TapGemmSmem<BN, STAGES, MT>;
+  using SM = TapGemmSmem<BN, STAGES, MT, NI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFFSET);
@@ -114,7 +119,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
     tma_prefetch_desc(&P.amap[2]);
     tma_prefetch_desc(&P.amap[3]);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    mbar_init(tmem_full, NI);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<SM::TMEM_COLS>(tmem_slot);
@@ -173,18 +178,21 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===== MMA issuer =====
+  } else if (threadIdx.x == 32 || (NI == 2 && threadIdx.x == 192)) {
+    // ===== MMA issuer(s): issuer `who` takes the ring stages who, who + NI, ... and owns accumulator set `who` =====
     constexpr uint32_t idesc = make_idesc(TC_BM, BN, 0, 0);
-    int s = 0; uint32_t ph = 0;
+    const int who = threadIdx.x == 32 ? 0 : 1;
+    int s = who; uint32_t ph = 0;                 // (NI <= STAGES)
     const uint32_t smem_base = smem_u32(smem);
+    const uint32_t acc_base = tmem_base + (uint32_t)(who * MT * BN);
     const bool thin_k = P.thin_k != 0, no_mma = (P.dbg_mode & 1) != 0;
-    for (int it = 0; it < iters; ++it) {
+    for (int it = who; it < iters; it += NI) {
       mbar_wait(&full_bar[s], ph);
       if (it == 0) DBG_T(2);
       tc_fence_after();
       const uint32_t a_addr = smem_base + s * SM::STAGE_BYTES;
       const uint32_t b_addr = a_addr + SM::A_BYTES;
+      const int first = it - who;                 // 0 on this issuer's first stage: its accumulators start from zero
       if (no_mma) { mbar_arrive(&empty_bar[s]); }
       else {
         if (thin_k) {
@@ -192,7 +200,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
           for (int k = 0; k < 4; ++k) {   // block k/2 (kernel row), 16 K-elements k%2 inside its 64-byte rows
             const uint64_t ad = make_smem_desc(a_addr + (k >> 1) * 8192 + (k & 1) * 32, 16, 512, 4);
             const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+            umma_bf16(acc_base, ad, bd, idesc, (first | k) != 0);
           }
         } else {
 #pragma unroll
@@ -201,16 +209,17 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
             for (int k = 0; k < TC_BK / 16; ++k) {
               const uint64_t ad = make_smem_desc(a_addr + mt * (TC_BM * TC_BK * 2) + k * 32, 16, 1024);
               const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(tmem_base + (uint32_t)(mt * BN), ad, bd, idesc, (it | k) != 0);
+              umma_bf16(acc_base + (uint32_t)(mt * BN), ad, bd, idesc, (first | k) != 0);
             }
         }
         umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
       }
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      s += NI;
+      if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
     }
-    umma_commit(tmem_full);
-    DBG_T(3);
-  } else if (warp >= 2) {
+    umma_commit(tmem_full);           // one arrival per issuer: the barrier completes when every accumulator set is final
+    if (who == 0) DBG_T(3);
+  } else if (warp >= 2 && warp < 6) {
     // ===== epilogue: TMEM -> registers -> bias/activation -> bf16 NHWC =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     int row = q * 32 + lane;                // accumulator row = grid pixel inside the tile (first accumulator)
@@ -264,6 +273,12 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0), r);
+          if constexpr (NI == 2) {           // add the second issuer's accumulator
+            uint32_t r2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(MT * BN + mt * BN + c0), r2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          }
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint32_t w[4];
@@ -337,6 +352,12 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if constexpr (NI == 2) {
+          uint32_t r2[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(MT * BN + c0), r2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
 #pragma unroll
         for (int v = 0; v < 8; ++v) st_shared_v4(stg + c0 * 4 + v * 16, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
       }
@@ -963,24 +984,24 @@ static int dump_debug_times(const TapGemmParams& P0, dim3 grid, cudaStream_t st,
   return rc;
 }
 
-template <int BN, int STAGES, int MT = 1>
+template <int BN, int STAGES, int MT = 1, int NI = 1>
 static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st);
 
-template <int BN, int STAGES, int MT = 1>
+template <int BN, int STAGES, int MT = 1, int NI = 1>
 static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
-  return dump_debug_times(P, grid, st, BN, &launch_tapgemm_raw<BN, STAGES, MT>);
+  return dump_debug_times(P, grid, st, BN, &launch_tapgemm_raw<BN, STAGES, MT, NI>);
 }
 
-template <int BN, int STAGES, int MT>
+template <int BN, int STAGES, int MT, int NI>
 static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
-  using SM = TapGemmSmem<BN, STAGES, MT>;
+  using SM = TapGemmSmem<BN, STAGES, MT, NI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, MT, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  launch_k(tapgemm_tc_kernel<BN, STAGES, MT>, grid, 192, SM::TOTAL, st, P);
+  launch_k(tapgemm_tc_kernel<BN, STAGES, MT, NI>, grid, NI == 2 ? 224 : 192, SM::TOTAL, st, P);
   return finish_launch();
 }
 
@@ -1051,6 +1072,11 @@ static int wgrad_split_floor() {  // STCGAN_WGRAD_SPLIT_CEIL=1 restores the old 
 static int mt_mode() {            // STCGAN_TC_MT: unset = automatic, 1 = one accumulator per CTA always, 2 = two whenever possible
   const char* e = getenv("STCGAN_TC_MT");
   return !e ? 0 : (e[0] == '2' ? 2 : 1);
+}
+
+static int dual_issue_mode() {
+  const char* e = getenv("STCGAN_TC_DUAL");
+  return (e && e[0] == '1') ? 1 : 0;
 }
 
 static int bn256_auto() {         // STCGAN_TC_BN256_AUTO=0 disables the wave-aware choice of 128x256 tiles
@@ -1292,9 +1318,15 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   // STCGAN_TC_STAGES=n (experiments): force the ring depth (fewer stages = more resident CTAs per SM)
   int force = 0;
   { const char* e = getenv("STCGAN_TC_STAGES"); if (e) force = atoi(e); }
+  // STCGAN_TC_DUAL=1 (opt-in): two MMA issuer threads for 128-wide tiles.  Parity-green (tests/test_kernels_gpu.py with the
+  // variable set); measured per launch (tools/conv_probe.py): the lone-CTA launches gain (e4 fwd 29.4 -> 24.3 us), launches
+  // with two resident CTAs per SM do not (c4 dgrad 57.8 -> 59.9, e3 fwd 19.3 -> 19.6), and ONE of two probe runs ended in an
+  // unspecified launch failure that has not been reproduced or explained yet -- hence not a default
+  const bool dual = dual_issue_mode() && g.ntaps * P.kchunks >= 4;
   if (BN == 128) {
     if (force == 2) return launch_tapgemm<128, 2>(P, grid, st);
     if (force == 3) return launch_tapgemm<128, 3>(P, grid, st);
+    if (dual) return deep ? launch_tapgemm<128, 6, 1, 2>(P, grid, st) : launch_tapgemm<128, 3, 1, 2>(P, grid, st);
     return deep ? launch_tapgemm<128, 6>(P, grid, st) : launch_tapgemm<128, 3>(P, grid, st);
   }
   if (force == 2) return launch_tapgemm<64, 2>(P, grid, st);

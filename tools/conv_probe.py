@@ -49,8 +49,9 @@ def run(shape, reps=20):
     return us, fl / us / 1e6
 
 
-KEYS = ("STCGAN_TC_DBGMODE", "STCGAN_TC_STAGES", "STCGAN_TC_BN256", "STCGAN_TC_BN256_STAGES", "STCGAN_TC_MT", "STCGAN_TC_BN256_AUTO")
-envs = [{}, dict(STCGAN_TC_MT="1", STCGAN_TC_BN256_AUTO="0"), dict(STCGAN_TC_MT="2"), dict(STCGAN_TC_MT="1")]
+KEYS = ("STCGAN_TC_DBGMODE", "STCGAN_TC_STAGES", "STCGAN_TC_BN256", "STCGAN_TC_BN256_STAGES", "STCGAN_TC_MT", "STCGAN_TC_BN256_AUTO",
+        "STCGAN_TC_DUAL")
+envs = [{}, dict(STCGAN_TC_DUAL="1"), dict(STCGAN_TC_DUAL="1", STCGAN_TC_MT="1", STCGAN_TC_BN256_AUTO="0")]
 print(f"{'shape':34s} " + " ".join(f"{','.join(k[10:] + '=' + v for k, v in e.items()) or 'default':>16s}" for e in envs) + "   (us, TF/s-equivalent)")
 for sh in SHAPES:
     cells = []
