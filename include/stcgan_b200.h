@@ -124,7 +124,9 @@ int stcgan_tapwgrad(int geom, int dtype, int backend,
  * The first / last layers (Cin in {3,4,7}: stcgan_g.py:85-86 outermost, stcgan_d.py:22-23; Cout in {1,3}:
  * stcgan_g.py:93-95, stcgan_d.py:49-50) have one GEMM dimension below a tensor-core tile.  Three layouts keep them on
  * tcgen05 without inflating HBM traffic:
- *   thin N : N padded to 16 in the packed weights only (stcgan_pack_weight_pad16); output written straight to NCHW fp32
+ *   thin N : (a) stcgan_thin_col2im below -- the form the networks use: one pixel GEMM with the taps in N + in-CTA col2im;
+ *            (b) stcgan_tapconv_thin_n -- the earlier tap-GEMM form, kept for comparison (the networks no longer call it):
+ *            N padded to 16 in the packed weights only (stcgan_pack_weight_pad16); output written straight to NCHW fp32
  *            (bias + Tanh/Sigmoid fused) or to an 8-channel NHWC gradient tensor;
  *   thin K : the thin tensor is kept zero-bordered with 8 channels, so one 4x4xC window is 4 rows of 64 contiguous
  *            bytes; a 5-D TMA view turns it into two 128-byte K-chunks per output pixel (K = 128), weights packed
