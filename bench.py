@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """ST-CGAN hot-path benchmark (BASELINE.json metric: train images/sec at 256x256, 16 images per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|infer]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|train512|infer]
 
 One "step" = one full ST-CGAN train step (src/cgan.py:274-351, VisualLoss off): G1,G2 forward, D1,D2 forward x4
 each, both backward phases, two Adam updates, on one synthetic ISTD-shaped batch of 16 images per GPU.
 Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM (CUDA-graph replay);
 `e2e` = the same through the public API with HOST (pinned) inputs copied in and the losses read back every step.
 `--impl reference` times the CPU restatement of the reference (oracle port: the reference is pure Python/torch and
-cannot travel to the GPU box) on a bounded sample of the same workload, on all host threads.
+cannot travel to the GPU box) on the SAME workload (16 images per step, --steps / --warmup honoured; a wall-clock cap
+shortens the run only if the host is very slow, and the line says what ran), on all host threads.
+`--workload train512` = BASELINE configs[4] (512x512, 32 images per GPU), `--workload infer` = configs[3].
 """
 import argparse
 import json
@@ -27,6 +29,22 @@ import torch  # noqa: E402
 
 BATCH_PER_GPU, H, W = 16, 256, 256
 METRIC = "stcgan_train_images_per_sec_256x256_b16_per_gpu"
+# workload -> (images per GPU, H, W, metric, BASELINE.json config it restates)
+TRAIN_WORKLOADS = {
+    "train": (16, 256, 256, METRIC, "configs[1]/[2]"),
+    "train512": (32, 512, 512, "stcgan_train_images_per_sec_512x512_b32_per_gpu", "configs[4]"),
+}
+CPU_TIME_CAP_S = 240.0      # wall-clock bound of the CPU arm (the default --steps 20 --warmup 5 run stays below it)
+
+
+def train_config(workload, world):
+    """The `config` object of a train line -- shared verbatim by the b200 arm and the reference arm."""
+    import stcgan_oracle as O
+    b, h, w, _, which = TRAIN_WORKLOADS[workload]
+    return {"workload": f"ST-CGAN full train step {h}x{w}, {b} images/GPU (BASELINE {which}; cgan.py:274-351, VisualLoss off, "
+                        "MSE adversarial loss as executed, Adam beta=(0.5,0.999))",
+            "global_batch": b * world, "parallelism": f"dp{world}",
+            "algorithmic_gflop_per_image": O.train_step_flops(h, w) / 1e9}
 
 
 def measured_peaks():
@@ -73,38 +91,101 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_rate(batch, steps, train=True):
-    """images/s of the CPU oracle (port of the reference path) on all host threads; bounded sample."""
+def cpu_oracle_rate(batch, steps, warmup=1, h=H, w=W, cap_s=CPU_TIME_CAP_S):
+    """images/s of the CPU oracle (port of the reference's train step, src/cgan.py:274-351) on all host threads.
+    Runs `warmup` untimed + `steps` timed steps on `batch` images; stops early (after >= 1 timed step) only if the
+    wall-clock cap would be exceeded.  Returns (images/s, threads, timed steps run, warm-up steps run)."""
     import stcgan_oracle as O
     torch.set_num_threads(os.cpu_count())
     states = O.build_all_states()
     tr = O.OracleTrainer(states)
-    x, m, y = O.make_istd_batch(batch, H, W, seed=42)
-    tr.train_step(x, m, y) if train else tr.forward_only(x, m, y)          # warm-up
-    t0 = time.perf_counter()
+    x, m, y = O.make_istd_batch(batch, h, w, seed=42)
+    t_start = time.perf_counter()
+    w_run = 0
+    for _ in range(max(warmup, 1)):
+        tr.train_step(x, m, y)
+        w_run += 1
+        per = (time.perf_counter() - t_start) / w_run
+        if (w_run + 1 + steps) * per > cap_s and w_run >= 1:       # a slow host: keep the time for timed steps
+            break
+    done, t0 = 0, time.perf_counter()
     for _ in range(steps):
-        tr.train_step(x, m, y) if train else tr.forward_only(x, m, y)
+        tr.train_step(x, m, y)
+        done += 1
+        if time.perf_counter() - t_start + (time.perf_counter() - t0) / done > cap_s:
+            break
     dt = time.perf_counter() - t0
-    return batch * steps / dt, torch.get_num_threads()
+    return batch * done / dt, torch.get_num_threads(), done, w_run
 
 
 def run_reference(args, rank):
+    """The reference arm: the reference's own CPU implementation of the path (oracle port, kind "port") on the stated
+    workload -- the full per-GPU batch per step, --steps / --warmup honoured -- on all host threads.  Rank 0 only."""
     if rank != 0:
         return
-    sample_batch = 4
-    steps = max(1, min(args.steps, 3))
-    rate, cores = cpu_oracle_rate(sample_batch, steps)
+    wl = args.workload if args.workload in TRAIN_WORKLOADS else "train"
+    b, h, w, metric, _ = TRAIN_WORKLOADS[wl]
+    rate, cores, steps, warm = cpu_oracle_rate(b, max(1, args.steps), max(1, args.warmup), h, w)
+    sample = (f"{steps} timed + {warm} warm-up train steps on the full {b}-image {h}x{w} batch (oracle port of src/cgan.py:274-351 on "
+              "torch CPU ops, fp32; the reference is pure Python and does not travel to the GPU box)")
+    if steps != args.steps:
+        sample += f"; stopped early by the {CPU_TIME_CAP_S:.0f} s wall-clock cap (asked for {args.steps} steps)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": 1e3 * sample_batch / rate, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric, "value": rate, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * b / rate, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ST-CGAN full train step 256x256 (cgan.py:274-351, VisualLoss off), CPU, fp32"},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} train steps on {sample_batch} of the 16 images (oracle port of src/cgan.py:274-351 "
-                                   "on torch CPU ops; the reference is pure Python and does not travel to the GPU box)"},
+        "config": train_config(wl, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cudnn_baseline(dev, batch, h, w, steps=10, warmup=3):
+    """"The kernel to beat" (BASELINE.md section 5): the reference's train step executed by STOCK torch on the
+    same GPU -- ATen -> cuDNN convolutions / batch norm, torch.optim.Adam -- in the two forms a user of the reference could
+    run today: fp32 as written (cuDNN may use TF32, torch's default), and bf16 autocast + channels_last.  The arithmetic is
+    the oracle's functional restatement of the reference modules (the modules themselves do not exist on the GPU box); it is
+    a reported baseline, never part of the product path.  cudnn.benchmark is ON (the baseline's best case; the reference
+    itself runs with benchmark off / deterministic on, src/main.py:43-45, 90-91)."""
+    import stcgan_oracle as O
+    out = {}
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name in ("fp32", "bf16_autocast_channels_last"):
+            cl = name != "fp32"
+            states = {n: {k: (v.to(dev).contiguous(memory_format=torch.channels_last) if (cl and v.dim() == 4) else v.to(dev))
+                          for k, v in sd.items()} for n, sd in O.build_all_states().items()}
+            tr = O.OracleTrainer(states)
+            x, m, y = (t.to(dev) for t in O.make_istd_batch(batch, h, w, seed=42))
+            if cl:
+                x, m, y = (t.contiguous(memory_format=torch.channels_last) for t in (x, m, y))
+
+            def step():
+                if cl:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        tr.train_step(x, m, y)
+                else:
+                    tr.train_step(x, m, y)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            dt = e0.elapsed_time(e1) * 1e-3
+            out[name] = {"value": batch * steps / dt, "unit": "images/s", "ms_per_step": 1e3 * dt / steps, "steps": steps}
+            del tr, states
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = prev
+    out["what"] = ("reference train step through stock torch " + torch.__version__ + " / cuDNN "
+                   + str(torch.backends.cudnn.version()) + " on this GPU (eager, cudnn.benchmark on); same batch and image size")
+    return out
 
 
 def instrumented_breakdown(eng, x, m, y):
@@ -136,7 +217,7 @@ def instrumented_breakdown(eng, x, m, y):
         g2b = 0 if g2 is None else e
         return float((2 * e + g2b) * (2 if ss is not None else 1) + e)     # reduce pass + apply pass (+ dy)
 
-    big = lambda yy, *a, **k: "hbm_big" if yy.numel() * 2 >= 16 * 2 ** 20 else "hbm_small"
+    big = lambda yy, *a, **k: "big" if yy.numel() * 2 >= 16 * 2 ** 20 else "small"
     table = {
         "bn_fused_apply": (bn_apply_bytes, lambda *a, **k: "bn_fwd_" + big(*a, **k)),
         "bn_act_bwd": (bn_bwd_bytes, lambda *a, **k: "bn_bwd_" + big(*a, **k)),
@@ -202,9 +283,22 @@ def instrumented_breakdown(eng, x, m, y):
     return fam, e_all0.elapsed_time(e_all1) * 1e-3
 
 
+def ncu_traffic():
+    """DRAM traffic of the dominant kernel family from the committed ncu capture of this build (written by
+    tools/ncu_traffic.py from `ncu --set full` of one train step; bench.py itself never runs under a profiler)."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path))
+    except (OSError, ValueError):
+        return None
+
+
 def run_b200(args, rank, world, local_rank):
     import stcgan_b200 as S
     import stcgan_oracle as O
+    BATCH_PER_GPU, H, W, METRIC, _ = TRAIN_WORKLOADS[args.workload]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     pg = None
@@ -292,12 +386,17 @@ def run_b200(args, rank, world, local_rank):
         dt, dt_e2e, dt_u8, dt_e2e_sync = t.tolist()
     # the instrumented eager step contains the gradient all-reduces: every rank must run it
     fam, eager_s = instrumented_breakdown(eng, x, m, y)
+    if world > 1:
+        # graphs that hold NCCL work must be gone before destroy_process_group() (main() calls it after this returns)
+        eng.release_graphs()
+        torch.cuda.synchronize()
     if rank != 0:
         return
     peaks = measured_peaks()
     images = BATCH_PER_GPU * world * args.steps
     value, e2e_value = images / dt, images / dt_e2e
     flops_step = O.train_step_flops(H, W) * BATCH_PER_GPU
+    traffic = ncu_traffic() if args.workload == "train" else None
     # ---- roofline of the dominant kernel family, timed live with CUDA events ---------------------------------------
     tc_t = sum(v[0] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
     tc_f = sum(v[1] for k, v in fam.items() if k in ("conv_tc", "wgrad_tc"))
@@ -305,12 +404,10 @@ def run_b200(args, rank, world, local_rank):
     achieved = tc_f / tc_t / 1e12 if tc_t > 0 else 0.0
     roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tf_sustained"],
-            # DRAM bytes (read + write) of ONE profiled launch of the dominant kernel, `ncu --set full` (committed summary):
-            # D's c4 input gradient, tapgemm_tc_kernel<128,3> grid (128,2,1): 19.97 MB read + 0 written back during the launch
-            # (the 8.4 MB output stays in L2) against 28.3 MB algorithmic (15.7 MB input + 4.2 MB weights + 8.4 MB output)
-            "traffic": 19.97e6,
-            "traffic_note": "per launch of tapgemm_tc_kernel<128,3> grid (128,2,1) (c4 dgrad), profiles/r01_ncu_full_tapgemm_v2.csv; "
-                            "algorithmic 28.3 MB; tensor pipe active 57.7 % in that capture",
+            # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the same kernel family, per launch (mean over the
+            # launches of one train step), from the committed `ncu --set full` capture of this build -- or null
+            "traffic": (traffic or {}).get("dominant_family_bytes_per_launch"),
+            "traffic_note": (traffic or {}).get("note", "no ncu capture of this build committed (profiles/r02_ncu_traffic.json)"),
             "kernel": "tapgemm_tc_kernel + tapwgrad_tc_kernel (all full-width tcgen05 conv launches of one train step)",
             "eager_step_seconds": eager_s,
             "launches": tc_n, "flops_per_step": tc_f, "seconds_per_step": tc_t, "peak_source": peaks["source"] + ", sustained bf16",
@@ -320,24 +417,46 @@ def run_b200(args, rank, world, local_rank):
     # HBM-bound families of the same instrumented step (algorithmic bytes / CUDA-event time; "big" = tensors >= 16 MB,
     # i.e. launches long enough for the rate to mean something -- the small ones are latency-bound and L2-resident)
     hb = {k: v for k, v in fam.items() if k.startswith(("bn_", "adam"))}
-    sel = [v for k, v in hb.items() if k.endswith("_big") or k == "adam"]
+    sel = list(hb.values())            # ALL BatchNorm launches (small, latency-bound ones included) + Adam
     hbm_t, hbm_b = sum(v[0] for v in sel), sum(v[1] for v in sel)
+    bn_sel = [v for k, v in hb.items() if k.startswith("bn_")]
+    bn_t, bn_b = sum(v[0] for v in bn_sel), sum(v[1] for v in bn_sel)
     roof_hbm = {"bound": "hbm", "achieved": hbm_b / hbm_t / 1e9 if hbm_t > 0 else 0.0, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": (hbm_b / hbm_t / 1e9 / peaks["hbm"]) if hbm_t > 0 else 0.0, "traffic": None,
-                "kernel": "bn_fused_apply + bn_bwd_reduce/apply on tensors >= 16 MB, adam_kernel (one train step)",
+                "kernel": "every bn_fused_apply / bn_bwd_reduce / bn_bwd_apply launch + adam_kernel of one train step "
+                          "(algorithmic bytes / CUDA-event time, single-stream instrumented step)",
+                "batchnorm_only": {"GBps": bn_b / bn_t / 1e9 if bn_t > 0 else 0.0, "frac": (bn_b / bn_t / 1e9 / peaks["hbm"]) if bn_t > 0 else 0.0,
+                                   "seconds_per_step": bn_t, "launches": sum(v[2] for v in bn_sel)},
                 "peak_source": peaks["source"],
                 "families": {k: {"s": v[0], "bytes": v[1], "launches": v[2], "GBps": v[1] / v[0] / 1e9 if v[0] > 0 else 0.0}
                              for k, v in hb.items()}}
-    cpu_rate, cores = cpu_oracle_rate(2, 2) if world == 1 else (None, None)
+    for v in loss_host[:6].tolist():
+        if not (v == v and abs(v) < 1e6):
+            raise SystemExit(f"bench.py: non-finite / diverged loss in the timed run: {loss_host.tolist()}")
+    cpu = cudnn = None
+    if world == 1:
+        # the CPU arm on the SAME workload (full per-GPU batch per step), bounded to ~10-30 s: 1 warm-up + 2 timed steps
+        cb, ch, cw = (BATCH_PER_GPU, H, W) if args.workload == "train" else (4, H, W)
+        rate, cores, done, warm = cpu_oracle_rate(cb, 2 if args.workload == "train" else 1, 1, ch, cw, cap_s=60.0)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{done} timed + {warm} warm-up train steps on {cb} of the {BATCH_PER_GPU} images per step at {ch}x{cw} "
+                         "(oracle port of src/cgan.py:274-351, torch CPU fp32, all host threads)"}
+        if not args.no_cudnn_baseline:
+            eng.release_graphs()
+            del eng, nets
+            torch.cuda.empty_cache()
+            cudnn = cudnn_baseline(dev, BATCH_PER_GPU, H, W)
+    cfg = train_config(args.workload, world)
+    cfg.update({"precision": "bf16 activations/weights, fp32 master weights + Adam + accumulation",
+                "l2": "per-step working set (>2 GB of activations and weights) exceeds the 126 MB L2; no explicit flush",
+                "cuda_graph": True,
+                "streams": "generator chain + four discriminator chains on five streams, weight-gradient kernels on side streams "
+                           "(fork/join inside the one captured graph; gradient all-reduces inside the graph at N > 1)"})
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ST-CGAN full train step 256x256, 16 images/GPU (BASELINE configs[1]; cgan.py:274-351, VisualLoss off, "
-                               "MSE adversarial loss as executed, Adam beta=(0.5,0.999)), bf16 activations/weights, fp32 master+Adam",
-                   "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}", "l2": "per-step working set (>2 GB of activations "
-                   "and weights) exceeds the 126 MB L2; no explicit flush", "cuda_graph": True, "streams": "D1 / D2 / generator chains on three streams, weight-gradient kernels on side streams (fork/join inside the graph)",
-                   "algorithmic_gflop_per_image": O.train_step_flops(H, W) / 1e9},
+        "config": cfg,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host),
                 "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": 1e3 * dt_e2e / args.steps,
                 "api": "STCGANEngine.replay_async(x, m, y) on pinned float32 host batches: every step's inputs are copied H2D "
@@ -352,9 +471,10 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
         "losses_last_step": dict(zip(S.engine.SLOTS, [float(v) for v in loss_host[:6]])),
     }
-    if cpu_rate is not None:
-        line["cpu_baseline"] = {"value": cpu_rate, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": "2 train steps on 2 of the 16 images (oracle port of src/cgan.py:274-351, torch CPU fp32)"}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    if cudnn is not None:
+        line["cudnn_baseline"] = cudnn
     print(json.dumps(line), flush=True)
 
 
@@ -424,7 +544,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "infer"])
+    ap.add_argument("--workload", default="train", choices=["train", "train512", "infer"])
+    ap.add_argument("--no-cudnn-baseline", action="store_true", help="skip the stock torch/cuDNN arm (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -443,6 +564,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

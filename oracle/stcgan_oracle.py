@@ -12,7 +12,7 @@ itself run in the build container*:
   * `oracle/pin_against_reference.py` imports the unmodified modules from
     /root/reference and checks every function below against them bit-for-bit;
   * `tests/golden/make_golden.py` (committed) ran the reference modules and
-    wrote `tests/golden/*.npz`; `tests/test_oracle_golden.py` re-checks this
+    wrote `tests/golden/*.npz`; `tests/test_cpu.py` re-checks this
     oracle against those fixtures everywhere (the GPU box has no /root/reference).
 
 Reference lines each function follows are cited in its docstring
@@ -187,6 +187,68 @@ def trainable_keys(sd):
 
 
 # --------------------------------------------------------------------------
+# optional reduced-precision emulation of the convolutions (test infrastructure for the bf16 parity bounds)
+# --------------------------------------------------------------------------
+_EMULATE = None     # None = exact arithmetic of the tensors' dtype; torch.bfloat16 = see `emulate_conv_precision`
+
+
+class emulate_conv_precision:
+    """Context manager: every convolution rounds its input, its weight, its OUTPUT and the incoming output-gradient to
+    `dtype` (values stay stored in the surrounding float32 / float64 tensors; products and sums are exact in that wider
+    type).  This is the arithmetic model of a bf16 tensor-core pipeline with bf16 activation storage and fp32 accumulation
+    and parameters; running the otherwise unchanged restatement under it gives the error that rounding alone causes
+    (14-31 % on end-to-end gradients through gate flips), against which a CUDA bf16 path is bounded."""
+
+    def __init__(self, dtype=torch.bfloat16):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _EMULATE
+        self.prev, _EMULATE = _EMULATE, self.dtype
+
+    def __exit__(self, *a):
+        global _EMULATE
+        _EMULATE = self.prev
+
+
+class _RoundSTE(torch.autograd.Function):
+    """forward: round to `dtype`; backward: identity (the rounding of gradients is explicit, see _RoundGrad)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _RoundGrad(torch.autograd.Function):
+    """forward: identity; backward: round the gradient to `dtype`."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).to(g.dtype), None
+
+
+def _conv(fn, x, w, bias, stride, pad, last=False):
+    """`last`: the network's output layer, whose result (and incoming gradient) stay in float32 in the modelled pipeline."""
+    if _EMULATE is None:
+        return fn(x, w, bias, stride, pad)
+    y = fn(_RoundSTE.apply(x, _EMULATE), _RoundSTE.apply(w, _EMULATE), None, stride, pad)
+    if not last:
+        y = _RoundGrad.apply(y, _EMULATE)
+    if bias is not None:
+        y = y + bias.view(1, -1, 1, 1)
+    return y if last else _RoundSTE.apply(y, _EMULATE)
+
+
+# --------------------------------------------------------------------------
 # forward passes (functional; autograd tracks through `sd` tensors)
 # --------------------------------------------------------------------------
 
@@ -217,13 +279,13 @@ def generator_forward(sd, x, training=True, num_downs=8):
             if ph or pw:
                 h = F.pad(h, (0, pw, 0, ph))
             h = F.leaky_relu(h, LEAK)
-        h = F.conv2d(h, sd[kd + ".weight"], None, 2, 1)
+        h = _conv(F.conv2d, h, sd[kd + ".weight"], None, 2, 1)
         if kdn:
             h = _bn(sd, kdn, h, training)
     for level in range(num_downs, 0, -1):
         _, _, ku, kun = generator_keys(level, num_downs)
         h = F.relu(h)
-        h = F.conv_transpose2d(h, sd[ku + ".weight"], sd.get(ku + ".bias"), 2, 1)
+        h = _conv(F.conv_transpose2d, h, sd[ku + ".weight"], sd.get(ku + ".bias"), 2, 1, last=level == 1)
         if level == 1:
             return torch.tanh(h)
         h = _bn(sd, kun, h, training)
@@ -238,7 +300,7 @@ def discriminator_forward(sd, x, training=True, n_layers=3, use_sigmoid=False, n
     layers = discriminator_layers(x.size(1), ndf, n_layers)
     h = x
     for n, (i, cin, cout, stride, bias, bn_i) in enumerate(layers):
-        h = F.conv2d(h, sd[f"model.{i}.weight"], sd.get(f"model.{i}.bias"), stride, 1)
+        h = _conv(F.conv2d, h, sd[f"model.{i}.weight"], sd.get(f"model.{i}.bias"), stride, 1, last=n == len(layers) - 1)
         if bn_i is not None:
             h = _bn(sd, f"model.{bn_i}", h, training)
         if n != len(layers) - 1:
@@ -327,6 +389,8 @@ class HyperParams:
     lambda1: float = 5.0
     lambda2: float = 0.5
     lambda3: float = 0.5
+    lambda4: float = 0.0    # weights of vis1 / vis2 (cgan.py:347-348; reference default 5 / 50, needs VGG19 weights)
+    lambda5: float = 0.0
     ls: bool = False        # what `args.D_loss_fn == "leastsqure"` evaluates to (cgan.py:147)
     rel: bool = False
     avg: bool = False
@@ -337,8 +401,9 @@ class OracleTrainer:
     runs the step body of CGAN.run_epoch (src/cgan.py:274-351) with
     lambda4 = lambda5 = 0."""
 
-    def __init__(self, states, hp: HyperParams = HyperParams(), dtype=torch.float32):
+    def __init__(self, states, hp: HyperParams = HyperParams(), dtype=torch.float32, visual_loss=None):
         self.hp = hp
+        self.visual_loss = visual_loss     # callable (pred, target) -> scalar standing in for VisualLoss (loss.py:29-56)
         self.sd = OrderedDict()
         for name, sd in states.items():
             self.sd[name] = OrderedDict(
@@ -417,6 +482,11 @@ class OracleTrainer:
         g1 = adv(c1_real, c1_fake, False); g2 = adv(c2_real, c2_fake, False)         # :329-330
         data1 = data_loss(m_pred, m); data2 = data_loss(y_pred, y)                   # :332-333
         g_loss = data1 + hp.lambda1 * data2 + hp.lambda2 * g1 + hp.lambda3 * g2      # :343-348
+        if self.visual_loss is not None:                                             # :334-336, 347-348
+            vis1 = self.visual_loss(m_pred.expand(-1, 3, -1, -1), m.expand(-1, 3, -1, -1))
+            vis2 = self.visual_loss(y_pred, y)
+            g_loss = g_loss + hp.lambda4 * vis1 + hp.lambda5 * vis2
+            out.update(vis1_loss=vis1.detach(), vis2_loss=vis2.detach())
         g_loss.backward()                                                            # :350
         if keep_grads:
             out["grads_G"] = {n: [p.grad.detach().clone() for p in self.params[n]] for n in ("G1", "G2")}
@@ -428,6 +498,70 @@ class OracleTrainer:
                    G1_loss=g1.detach(), G2_loss=g2.detach(), data1_loss=data1.detach(),
                    data2_loss=data2.detach(), G_loss=g_loss.detach())
         return out
+
+
+class OracleDataParallel:
+    """Single-process statement of the data-parallel step (nn.DataParallel semantics of src/cgan.py:78-84):
+    every shard goes through its OWN forward (per-replica BatchNorm batch statistics and running buffers), the loss of a
+    shard is the mean over that shard, parameter gradients are the average over shards, ONE Adam update is applied to the
+    shared parameters.  `shards` = list of (x, m, y).  Returns per-shard outputs of `OracleTrainer.train_step`'s keys plus
+    the averaged gradients."""
+
+    def __init__(self, states, world, hp: HyperParams = HyperParams(), dtype=torch.float32):
+        self.t = OracleTrainer(states, hp, dtype)
+        self.world, self.hp = world, hp
+        # shard r sees the shared parameter tensors and its own copy of the BatchNorm buffers
+        self.views = []
+        for r in range(world):
+            v = OrderedDict()
+            for name, sd in self.t.sd.items():
+                keys = set(trainable_keys(sd))
+                v[name] = OrderedDict((k, (t_ if k in keys else t_.clone())) for k, t_ in sd.items())
+            self.views.append(v)
+
+    def train_step(self, shards, keep_grads=True):
+        hp, t, W = self.hp, self.t, self.world
+        adv = lambda r, f, d: adversarial_loss(r, f, d, hp.ls, hp.rel, hp.avg)
+        outs = [dict() for _ in shards]
+        t.optim_D.zero_grad(); t.optim_G.zero_grad()
+        t._req(("D1", "D2"), True)
+        held, total = [], 0.0
+        for o, sd, (x, m, y) in zip(outs, self.views, shards):
+            c1r = discriminator_forward(sd["D1"], torch.cat((x, m), 1))
+            mp = generator_forward(sd["G1"], x)
+            c1f = discriminator_forward(sd["D1"], torch.cat((x, mp.detach()), 1))
+            c2r = discriminator_forward(sd["D2"], torch.cat((x, m, y), 1))
+            yp = generator_forward(sd["G2"], torch.cat((x, mp), 1))
+            c2f = discriminator_forward(sd["D2"], torch.cat((x, mp.detach(), yp.detach()), 1))
+            d1, d2 = adv(c1r, c1f, True), adv(c2r, c2f, True)
+            total = total + (hp.lambda2 * d1 + hp.lambda3 * d2) / W
+            o.update(D1_loss=d1.detach(), D2_loss=d2.detach())
+            held.append((mp, yp))
+        total.backward()
+        grads = {}
+        if keep_grads:
+            grads.update({n: [p.grad.detach().clone() for p in t.params[n]] for n in ("D1", "D2")})
+        t.optim_D.step()
+        t.optim_G.zero_grad()
+        t._req(("D1", "D2"), False)
+        total = 0.0
+        for o, sd, (x, m, y), (mp, yp) in zip(outs, self.views, shards, held):
+            c1r = discriminator_forward(sd["D1"], torch.cat((x, m), 1))
+            c1f = discriminator_forward(sd["D1"], torch.cat((x, mp), 1))
+            c2r = discriminator_forward(sd["D2"], torch.cat((x, m, y), 1))
+            c2f = discriminator_forward(sd["D2"], torch.cat((x, mp, yp), 1))
+            g1, g2 = adv(c1r, c1f, False), adv(c2r, c2f, False)
+            da1, da2 = data_loss(mp, m), data_loss(yp, y)
+            gl = da1 + hp.lambda1 * da2 + hp.lambda2 * g1 + hp.lambda3 * g2
+            total = total + gl / W
+            o.update(m_pred=mp.detach(), y_pred=yp.detach(), G1_loss=g1.detach(), G2_loss=g2.detach(),
+                     data1_loss=da1.detach(), data2_loss=da2.detach(), G_loss=gl.detach())
+        total.backward()
+        if keep_grads:
+            grads.update({n: [p.grad.detach().clone() for p in t.params[n]] for n in ("G1", "G2")})
+        t.optim_G.step()
+        t._req(("D1", "D2"), True)
+        return outs, grads
 
 
 def float2uint(array):

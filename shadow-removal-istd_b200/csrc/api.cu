@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 namespace stcgan {
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 int pdl_enabled() {
   static int v = -1;
@@ -88,8 +88,8 @@ const char* stcgan_error_string(int code) {
   return "stcgan: unknown error";
 }
 
-int64_t stcgan_launch_count(void) { return g_launches; }
-void stcgan_launch_count_reset(void) { g_launches = 0; }
+int64_t stcgan_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void stcgan_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int IH, int IW, int K, int ldx,
                    const void* wp, const float* bias, int act, void* y, int OH, int OW, int Nout, int ldy,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/stcgan_b200.h"
 
 namespace stcgan {
@@ -10,10 +11,12 @@ namespace stcgan {
 // ---------------------------------------------------------------------------------------------
 // launch accounting + error plumbing
 // ---------------------------------------------------------------------------------------------
-extern int64_t g_launches;
+// (a relaxed atomic: launches may be issued from several host threads -- one per device under nn.DataParallel-style callers;
+// it is a statistics counter only, no kernel or host logic depends on its value)
+extern std::atomic<int64_t> g_launches;
 
 inline int finish_launch() {
-  ++g_launches;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

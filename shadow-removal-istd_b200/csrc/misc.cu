@@ -616,7 +616,7 @@ static int adam_update(const stcgan_adam_tensor* table, const int32_t* blocks, i
   if (nblocks <= 0) return STCGAN_EINVAL;
   if (tick) {
     launch_k(adam_tick_kernel, 1, 1, 0, st, hyper);
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   static bool configured = false;
   if (!configured) {

@@ -17,7 +17,9 @@ bucket while G1's backward is still running.  The whole step can be captured int
 """
 from __future__ import annotations
 
+import atexit
 import os
+import weakref
 from dataclasses import dataclass
 
 import torch
@@ -25,7 +27,22 @@ import torch
 from . import _lib, ops
 from .optim import FusedAdam
 
-SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss")
+SLOTS = ("D1_loss", "D2_loss", "G1_loss", "G2_loss", "data1_loss", "data2_loss", "vis1_loss", "vis2_loss")
+
+_LIVE_ENGINES = weakref.WeakSet()
+
+
+def _release_all_graphs():
+    """atexit: captured graphs that contain NCCL collectives must be destroyed before the process group / the CUDA context
+    go away (torch 2.11 + NCCL 2.28 otherwise hang in destroy_process_group() or at interpreter exit)."""
+    for e in list(_LIVE_ENGINES):
+        try:
+            e.release_graphs()
+        except Exception:
+            pass
+
+
+atexit.register(_release_all_graphs)
 
 
 class _Lanes:
@@ -50,10 +67,22 @@ class _Lanes:
         if self.streams:
             self.streams[i % len(self.streams)].wait_stream(torch.cuda.current_stream())
 
+    def wait_lane(self, i, j):
+        """lane i waits for everything issued so far on lane j"""
+        if self.streams and i % len(self.streams) != j % len(self.streams):
+            self.streams[i % len(self.streams)].wait_stream(self.streams[j % len(self.streams)])
+
     def join(self):
         cur = torch.cuda.current_stream()
         for s in self.streams:
             cur.wait_stream(s)
+
+    def join_lanes(self, idx):
+        """the current stream waits for the given lanes only"""
+        if self.streams:
+            cur = torch.cuda.current_stream()
+            for i in idx:
+                cur.wait_stream(self.streams[i % len(self.streams)])
 
     def record(self, i):
         """event after everything issued so far on lane i (None when the lanes are disabled: program order suffices)"""
@@ -101,7 +130,16 @@ class GradientSync:
 
 @dataclass
 class TrainConfig:
-    """Defaults of src/main.py:182-239; `ls` is what `args.D_loss_fn == "leastsqure"` evaluates to (always False)."""
+    """Hyper-parameters of the step.  lr / beta / lambda1..3 are the defaults of src/main.py:182-239; `ls` is what
+    `args.D_loss_fn == "leastsqure"` evaluates to (always False, src/cgan.py:147); `rel` / `avg` select the RpGAN / RaGAN
+    forms of AdversarialLoss (src/loss.py:88-96, 102-110; guild.yml:16-18 defaults to rel_avg).
+
+    lambda4 / lambda5 weight the VGG19 perceptual terms vis1 / vis2 (src/cgan.py:334-348).  NOTE: the reference's own
+    defaults are lambda4 = 5, lambda5 = 50 (src/main.py); they default to 0 HERE because `VisualLoss` needs pretrained
+    VGG19-BN weights that this package does not ship and does not compute.  Setting either to a non-zero
+    value requires passing `visual_loss=` (any differentiable torch callable `(pred, target) -> scalar`, e.g. the
+    reference's `src.loss.VisualLoss().cuda()`) to STCGANEngine: its value and its gradient w.r.t. m_pred / y_pred are
+    taken with torch autograd and added to the fused loss gradients before G2's / G1's backward."""
     lr_G: float = 5e-4
     lr_D: float = 1e-4
     beta1: float = 0.5
@@ -109,14 +147,27 @@ class TrainConfig:
     lambda1: float = 5.0
     lambda2: float = 0.5
     lambda3: float = 0.5
+    lambda4: float = 0.0
+    lambda5: float = 0.0
     ls: bool = False
-    skip_dead_real_passes: bool = False   # True drops the two G-phase `real` D passes (changes D's running stats only)
+    rel: bool = False
+    avg: bool = False
+    skip_dead_real_passes: bool = False   # True drops the two G-phase `real` D passes (changes D's running stats only;
+                                          # ignored for the relativistic losses, which need them)
 
 
 class STCGANEngine:
-    def __init__(self, G1, G2, D1, D2, cfg: TrainConfig = TrainConfig(), process_group=None):
+    def __init__(self, G1, G2, D1, D2, cfg: TrainConfig = TrainConfig(), process_group=None, visual_loss=None):
         self.nets = dict(G1=G1, G2=G2, D1=D1, D2=D2)
         self.cfg = cfg
+        if (cfg.lambda4 != 0 or cfg.lambda5 != 0) and visual_loss is None:
+            raise NotImplementedError(
+                "lambda4 / lambda5 weight the VGG19 perceptual loss (src/cgan.py:334-348, src/loss.py:29-56), which this "
+                "package does not implement (pretrained weights are not available offline): pass visual_loss=<torch "
+                "callable (pred, target) -> scalar>, e.g. the reference's VisualLoss().cuda(), or leave them at 0")
+        if cfg.avg and not cfg.rel:
+            raise ValueError("avg=True only has a meaning together with rel=True (src/loss.py:88-110)")
+        self.visual_loss = visual_loss
         for n in self.nets.values():
             if not next(n.parameters()).is_cuda:
                 raise RuntimeError("STCGANEngine needs the modules on a CUDA device (no CPU fallback)")
@@ -129,7 +180,7 @@ class STCGANEngine:
         # Concurrency inside the step (STCGAN_CONCURRENCY=0 turns all of it off, STCGAN_SIDE_STREAM=0 only the first):
         #  * every network's weight-gradient kernels run on its own side stream, next to the dgrad / BatchNorm chain
         #    (nets._wgrad_async);
-        #  * the D1 chain and the D2 chain of each phase run on two lanes next to the generator chain on the main stream --
+        #  * the D1 chain and the D2 chain of each phase run on lanes next to the generator chain on the main stream --
         #    they only meet at the loss kernels (cgan.py:281-302, 321-348 have no other cross-dependency).
         # All forks and joins are stream events, so the same code runs eagerly and under CUDA-graph capture.
         conc = os.environ.get("STCGAN_CONCURRENCY", "1") != "0"
@@ -144,9 +195,6 @@ class STCGANEngine:
         # graph (6.13 -> 6.25 ms, with the priority carried as a kernel launch attribute), so it is off by default
         hi = conc and os.environ.get("STCGAN_HI_PRIORITY", "0") == "1"
         self.hi_stream = torch.cuda.Stream(device=self.device, priority=-1) if hi else None
-        for st in list(self.side_streams.values()) + self.lanes.streams + [self.hi_stream]:
-            if st is not None:
-                ops.register_concurrent_stream(st)
         self.optim_G = FusedAdam(list(G1.parameters()) + list(G2.parameters()), lr=cfg.lr_G, betas=(cfg.beta1, cfg.beta2))
         self.optim_D = FusedAdam(list(D1.parameters()) + list(D2.parameters()), lr=cfg.lr_D, betas=(cfg.beta1, cfg.beta2))
         self.optim_G.set_packed_grads({**self.rt["G1"].param_grad_views, **self.rt["G2"].param_grad_views})
@@ -168,8 +216,10 @@ class STCGANEngine:
         self.optim_G.grad_scale = self.optim_D.grad_scale = 1.0 / self.world
         self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._graph = None
+        self._graphs = []
         self._static = None
         self.last = {}
+        _LIVE_ENGINES.add(self)
 
     def _critical(self):
         """Context: issue on the high-priority stream (forked from / joined into the current stream)."""
@@ -188,81 +238,152 @@ class STCGANEngine:
         return ctx()
 
     # ------------------------------------------------------------------------------------------
+    # adversarial objectives (src/loss.py:86-112) as launches of the fused loss kernel; they return the gradients
+    # w.r.t. C_real / C_fake (None where the caller does not need one) and accumulate the loss value into `slot`
+    # ------------------------------------------------------------------------------------------
+    def _labels(self):
+        cfg = self.cfg
+        return (ops.KIND_BCE if cfg.ls else ops.KIND_MSE), 1.0, (-1.0 if cfg.ls else 0.0)
+
+    def _rel_terms(self, c_real, c_fake, d_loss, lam, slot):
+        """RpGAN / RaGAN objective of one discriminator, D side (d_loss) or G side: value into `slot`, returns
+        (dL/dC_real, dL/dC_fake) scaled by `lam`."""
+        cfg = self.cfg
+        kind, real, fake = self._labels()
+        first, second = (c_real, c_fake) if d_loss else (c_fake, c_real)
+        if cfg.avg:     # loss.py:90-94 / 104-108: 0.5 * (cal(first - mean(second), real) + cal(second - mean(first), fake))
+            z1, z2 = ops.rel_logits(first, second, True), ops.rel_logits(second, first, True)
+            g1, g2 = torch.empty_like(z1), torch.empty_like(z2)
+            ops.fused_loss([dict(kind=kind, a=z1, grad=g1, target=real, weight=0.5 * lam, loss_weight=0.5, slot=slot),
+                            dict(kind=kind, a=z2, grad=g2, target=fake, weight=0.5 * lam, loss_weight=0.5, slot=slot)],
+                           self.losses)
+            # d/d first = g1 - mean_batch(g2),  d/d second = g2 - mean_batch(g1): the same kernel in its forward form
+            d_first, d_second = ops.rel_logits(g1, g2, True), ops.rel_logits(g2, g1, True)
+        else:           # loss.py:96 / 110: cal(first - second, real)
+            z = ops.rel_logits(first, second, False)
+            d_first = torch.empty_like(z)
+            ops.fused_loss([dict(kind=kind, a=z, grad=d_first, target=real, weight=lam, loss_weight=1.0, slot=slot)],
+                           self.losses)
+            d_second = ops.rel_logits(None, d_first, False, backward=True)
+        return (d_first, d_second) if d_loss else (d_second, d_first)
+
+    # ------------------------------------------------------------------------------------------
     def _step_segments(self, x, m, y):
-        """The train step as a generator: it yields the names of the networks whose flat gradient buffers must
-        be all-reduced before the next segment runs (data parallelism); each segment between two yields is pure
-        kernel launches and can be captured into a CUDA graph."""
+        """The train step as a generator: it yields gradient-exchange requests `(bucket names, blocking[, wait names])`
+        (data parallelism only) at the points where a bucket has become final; the consumer launches the all-reduce on the
+        stream that is CURRENT at the yield -- so a request raised inside a lane only orders that lane behind the
+        collective.  Everything between two yields is pure kernel launches; with the collectives launched through c10d's
+        stream events the whole generator can be consumed inside ONE CUDA-graph capture."""
         cfg, rt = self.cfg, self.rt
-        kind = ops.KIND_BCE if cfg.ls else ops.KIND_MSE
-        real, fake = 1.0, (-1.0 if cfg.ls else 0.0)
+        kind, real, fake = self._labels()
+        multi = self.world > 1
         newg = lambda t: torch.empty_like(t)
+        d1_params, d2_params = list(self.nets["D1"].parameters()), list(self.nets["D2"].parameters())
         # ================= D phase (cgan.py:278-305) =================
         L = self.lanes
         rt["D1"].zero_grads(); rt["D2"].zero_grads()
         # every distinct input concatenation (cgan.py:281-289, 321-324) is packed once per step and shared.
-        # Each of the four discriminator passes is an independent chain  forward -> its loss term -> backward  (the terms
-        # of D_loss are separable, and the backward passes only meet in atomic accumulations), so every pass runs on its
-        # own lane and starts the moment its inputs exist: the two `real` passes at once, D1's `fake` pass after G1's
+        # SGAN: each of the four discriminator passes is an independent chain  forward -> its loss term -> backward  (the
+        # terms of D_loss are separable, and the backward passes only meet in atomic accumulations), so every pass runs on
+        # its own lane and starts the moment its inputs exist: the two `real` passes at once, D1's `fake` pass after G1's
         # forward, D2's after G2's -- all of it underneath the generator chain on the main stream.  The only ordering kept
         # between the two passes of one discriminator is forward-after-forward: the BatchNorm running statistics are
-        # order-dependent (real first, as in the reference).
+        # order-dependent (real first, as in the reference).  Relativistic forms couple real and fake logits: there the
+        # `fake` lane runs  fake forward -> objective -> both backward passes.
         self.losses.zero_()
         L.fork()
 
-        def d_pass(net, sources, packed, target, lam, slot):
+        def d_real(net, sources, packed, lam, slot):
             c, w = rt[net].forward(sources, True, packed=packed)
-            after_fwd = L.record({"D1": 0, "D2": 1}[net]) if target == real else None
+            after_fwd = L.record({"D1": 0, "D2": 1}[net])
+            if cfg.rel:
+                return c, w, after_fwd
             d = newg(c)
-            ops.fused_loss([dict(kind=kind, a=c, grad=d, target=target, weight=0.5 * lam, loss_weight=0.5, slot=slot)],
+            ops.fused_loss([dict(kind=kind, a=c, grad=d, target=real, weight=0.5 * lam, loss_weight=0.5, slot=slot)],
                            self.losses)
             rt[net].backward(w, d, False)
-            return c, w, d, after_fwd
+            return c, None, after_fwd
+
+        def d_fake(net, sources, packed, lam, slot, c_real, w_real):
+            c, w = rt[net].forward(sources, True, packed=packed)
+            if cfg.rel:
+                d_r, d_f = self._rel_terms(c_real, c, True, lam, slot)
+                rt[net].backward(w_real, d_r, False)
+                rt[net].backward(w, d_f, False)
+                return c
+            d = newg(c)
+            ops.fused_loss([dict(kind=kind, a=c, grad=d, target=fake, weight=0.5 * lam, loss_weight=0.5, slot=slot)],
+                           self.losses)
+            rt[net].backward(w, d, False)
+            return c
 
         with L.lane(0):
             pk_xm = rt["D1"].pack_sources([x, m])
-            c1r, w1r, d1r, ev1 = d_pass("D1", [x, m], pk_xm, real, cfg.lambda2, 0)
+            c1r, w1r, ev1 = d_real("D1", [x, m], pk_xm, cfg.lambda2, 0)
         with L.lane(1):
             pk_xmy = rt["D2"].pack_sources([x, m, y])
-            c2r, w2r, d2r, ev2 = d_pass("D2", [x, m, y], pk_xmy, real, cfg.lambda3, 1)
+            c2r, w2r, ev2 = d_real("D2", [x, m, y], pk_xmy, cfg.lambda3, 1)
         with self._critical():
             mp, wg1 = rt["G1"].forward([x], True)
             pk_xmp = rt["D1"].pack_sources([x, mp])
             L.lane_wait(2)
             L.wait_event(2, ev1)
             with L.lane(2):
-                c1f, w1f, d1f, _ = d_pass("D1", [x, mp], pk_xmp, fake, cfg.lambda2, 0)
+                if cfg.rel:
+                    L.wait_lane(2, 0)         # the objective needs C1_real; its backward pass runs here as well
+                d_fake("D1", [x, mp], pk_xmp, cfg.lambda2, 0, c1r, w1r)
+                # D1 is complete long before D2 (whose fake pass needs G2's forward): its gradient bucket goes on the wire
+                # now, its share of optim_D.step (cgan.py:305) and its two G-phase forward passes (cgan.py:321-322, with
+                # the UPDATED discriminator) follow on this lane, all underneath G2's forward and D2's fake chain
+                L.wait_lane(2, 0)
+                if multi:
+                    yield ("D1",), True
+                self.optim_D.step_partial(d1_params, tick=True, last=False)
+                ev_tick = L.record(2)
+                c1r_g = None
+                if cfg.rel or not cfg.skip_dead_real_passes:
+                    c1r_g, _ = rt["D1"].forward([x, m], True, packed=pk_xm)       # cgan.py:321
+                c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)         # cgan.py:322
             share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
             yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
             pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
             L.lane_wait(3)
             L.wait_event(3, ev2)
             with L.lane(3):
-                c2f, w2f, d2f, _ = d_pass("D2", [x, mp, yp], pk_xmpyp, fake, cfg.lambda3, 1)
-        L.join()
+                if cfg.rel:
+                    L.wait_lane(3, 1)
+                d_fake("D2", [x, mp, yp], pk_xmpyp, cfg.lambda3, 1, c2r, w2r)
+        # D2's bucket is the one on the critical path: D2 fake chain -> all-reduce -> its Adam share -> G-phase D2 forwards
+        L.join_lanes((1, 3))
         self.last = dict(m_pred=mp, y_pred=yp)
-        del w1r, w1f, w2r, w2f
-        if self.world > 1:          # (single GPU: no exchange, the whole step is one CUDA graph)
-            yield ("D1", "D2"), True                          # blocking: optim_D needs the reduced gradients
-        self.optim_D.step()                                   # cgan.py:305
+        del w1r, w2r
+        if multi:
+            yield ("D2",), True
+        if ev_tick is not None:
+            torch.cuda.current_stream().wait_event(ev_tick)      # the step counter advanced with D1's share
+        self.optim_D.step_partial(d2_params, tick=False, last=True)           # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
-        L.fork()
-        with L.lane(0):
-            if not cfg.skip_dead_real_passes:
-                rt["D1"].forward([x, m], True, packed=pk_xm)      # cgan.py:321 (BatchNorm running-stat side effect only)
-            c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)        # cgan.py:322
-        with L.lane(1):
-            if not cfg.skip_dead_real_passes:
-                rt["D2"].forward([x, m, y], True, packed=pk_xmy)  # cgan.py:323
-            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)  # cgan.py:324
-        L.join()
-        dm, dy, d1f, d2f = newg(mp), newg(yp), newg(c1f), newg(c2f)
-        ops.fused_loss([
-            dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),
-            dict(kind=ops.KIND_L1, a=yp, b=y, grad=dy, weight=cfg.lambda1, loss_weight=1.0, slot=5),
-            dict(kind=kind, a=c1f, grad=d1f, target=real, weight=cfg.lambda2, loss_weight=1.0, slot=2),
-            dict(kind=kind, a=c2f, grad=d2f, target=real, weight=cfg.lambda3, loss_weight=1.0, slot=3),
-        ], self.losses)
+        c2r_g = None
+        if cfg.rel or not cfg.skip_dead_real_passes:
+            c2r_g, _ = rt["D2"].forward([x, m, y], True, packed=pk_xmy)          # cgan.py:323 (SGAN: running stats only)
+        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)           # cgan.py:324
+        L.join()                                                                  # D1's G-phase passes (lane 2)
+        dm, dy = newg(mp), newg(yp)
+        terms = [dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),
+                 dict(kind=ops.KIND_L1, a=yp, b=y, grad=dy, weight=cfg.lambda1, loss_weight=1.0, slot=5)]
+        if cfg.rel:
+            ops.fused_loss(terms, self.losses)
+            _, d1f = self._rel_terms(c1r_g, c1f, False, cfg.lambda2, 2)          # loss.py:102-110
+            _, d2f = self._rel_terms(c2r_g, c2f, False, cfg.lambda3, 3)
+        else:
+            d1f, d2f = newg(c1f), newg(c2f)
+            ops.fused_loss(terms + [
+                dict(kind=kind, a=c1f, grad=d1f, target=real, weight=cfg.lambda2, loss_weight=1.0, slot=2),
+                dict(kind=kind, a=c2f, grad=d2f, target=real, weight=cfg.lambda3, loss_weight=1.0, slot=3),
+            ], self.losses)
+        if self.visual_loss is not None and (cfg.lambda4 != 0 or cfg.lambda5 != 0):
+            self._visual_terms(mp, yp, m, y, dm, dy)
         L.fork()
         with L.lane(0):
             di1 = rt["D1"].backward(w1f, d1f, True, param_grads=False)  # dgrad only: D is frozen (cgan.py:317-318)
@@ -274,14 +395,14 @@ class STCGANEngine:
         with self._critical():
             dig2 = rt["G2"].backward(wg2, dy, True)
             ops.unpack_input_grad(dig2, 3, 1, dm, True)       # G2's input gradient, mask channel (cgan.py:286)
-        if self.world > 1:
+        if multi:
             yield ("G2",), False                              # async: overlaps G1's backward
         # G1's backward in two halves: after the decoder half its up-conv weight gradients (64 % of G1's parameters) are
         # final and go on the wire under the encoder half; by then G2's sum has landed, so G2's share of optim_G.step
         # (cgan.py:351; an HBM-bound stream over 28 B/parameter) runs on a lane underneath the encoder half as well
         with self._critical():
             rt["G1"].backward(wg1, dm, False, part="dec")
-        if self.world > 1:
+        if multi:
             yield ("G1.ups",), False, ("G2",)
         split = bool(L.streams)
         if split:
@@ -293,19 +414,35 @@ class STCGANEngine:
             rt["G1"].backward(wg1, dm, False, part="enc")
         if split:
             L.join()
-        if self.world > 1:
+        if multi:
             yield ("G1.rest",), False, ("G1.ups",)            # the last bucket goes on the wire ...
         if split:
             self.optim_G.step_partial(self._g1_ups, tick=False, last=False)      # ... under the update of the bucket before it
-            if self.world > 1:
+            if multi:
                 yield (), True
             self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
         else:
-            if self.world > 1:
+            if multi:
                 yield (), True
             self.optim_G.step()                               # cgan.py:351
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step
+
+    def _visual_terms(self, mp, yp, m, y, dm, dy):
+        """vis1 / vis2 of src/cgan.py:334-348 through the user-supplied torch callable: values into slots 6 / 7, gradients
+        (torch autograd) added to dm / dy.  This is the one place where the engine runs foreign torch code."""
+        cfg = self.cfg
+        with torch.enable_grad():
+            mp_, yp_ = mp.detach().requires_grad_(True), yp.detach().requires_grad_(True)
+            v1 = self.visual_loss(mp_.expand(-1, 3, -1, -1), m.expand(-1, 3, -1, -1))
+            v2 = self.visual_loss(yp_, y)
+            g_m, g_y = torch.autograd.grad(cfg.lambda4 * v1 + cfg.lambda5 * v2, (mp_, yp_), allow_unused=True)
+        self.losses[6:7].copy_(v1.detach().reshape(1))
+        self.losses[7:8].copy_(v2.detach().reshape(1))
+        if g_m is not None:
+            dm.add_(g_m)
+        if g_y is not None:
+            dy.add_(g_y)
 
     def _reduce(self, req, pending):
         names, blocking = req[0], req[1]
@@ -324,10 +461,15 @@ class STCGANEngine:
         return self.losses
 
     def capture(self, x, m, y, warmup=3):
-        """Capture the train step for inputs of this shape: one CUDA graph per segment (the gradient all-reduces
-        of the data-parallel path run between graphs, on NCCL's stream)."""
+        """Capture the train step for inputs of this shape into ONE CUDA graph.  Under data parallelism the gradient
+        all-reduces are part of the graph: NCCL's stream joins the capture through the events c10d records around every
+        collective, so there are no host-side segment boundaries and the collectives overlap whatever else the graph has in
+        flight (measured on 2 x B200 in round 1: 7.33 -> 6.69 ms per step against graph segments with host-driven
+        all-reduces between them).  Such a graph holds NCCL work: call release_graphs() before destroy_process_group()
+        (an atexit hook does it for engines that are still alive).  STCGAN_NCCL_IN_GRAPH=0 keeps the multi-GPU step eager
+        (no graph at all; `replay` then simply runs train_step on the static inputs)."""
         self._static = tuple(t.contiguous().clone() for t in (x, m, y))
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -336,57 +478,62 @@ class STCGANEngine:
         torch.cuda.synchronize()
         self.optim_D.prepare(); self.optim_G.prepare()
         before = _lib.launch_count()
-        gen = self._step_segments(*self._static)
-        self._graphs, pool, pending = [], None, []
-        if self.world > 1 and os.environ.get("STCGAN_NCCL_IN_GRAPH", "0") == "1":
-            # OPT-IN: the gradient all-reduces are captured INTO the graph (NCCL's stream joins the capture through the
-            # events c10d records around every collective): one graph per step, no host-side segment boundaries, and the
-            # collectives overlap whatever else the graph has in flight.  Measured on 2 x B200: 7.33 -> 6.69 ms per step,
-            # replicas bit-identical -- but with torch 2.11 / NCCL 2.28 the processes then hang in
-            # destroy_process_group() / at exit (call release_graphs() first; not yet verified to be sufficient), so the
-            # default stays one graph per segment with the collectives between them
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for req in gen:
-                    self._reduce(req, pending)
-            self._graphs.append((g, None))
+        self._graphs, pending = [], []
+        if self.world > 1 and os.environ.get("STCGAN_NCCL_IN_GRAPH", "1") == "0":
+            self.train_step(*self._static)
             self.graph_launches = _lib.launch_count() - before
-            self._graph = True
-            return self._graphs
-        while True:
+            self._graph = "eager"
+        else:
             g = torch.cuda.CUDAGraph()
-            req = None
-            with torch.cuda.graph(g, pool=pool):
-                try:
-                    req = next(gen)
-                except StopIteration:
-                    pass
-            pool = g.pool()
-            self._graphs.append((g, req))
-            if req is None:
-                break
-            self._reduce(req, pending)                # keep ranks in lock-step during capture as well
-        self.graph_launches = _lib.launch_count() - before
-        self._graph = True
+            with torch.cuda.graph(g, stream=s):            # the warm-up stream: per-stream scratch already exists
+                for req in self._step_segments(*self._static):
+                    self._reduce(req, pending)
+            self._graphs.append(g)
+            self.graph_launches = _lib.launch_count() - before
+            self._graph = "graph"
+        self._capture_state = self._state_signature()
         return self._graphs
+
+    def _state_signature(self):
+        return (self.optim_D.generation, self.optim_G.generation, tuple(id(n._rt) for n in self.nets.values()),
+                sum(p._version for n in self.nets.values() for p in n.parameters()))
+
+    def _validate_capture(self):
+        """A captured graph bakes in device addresses (weights, packed bf16 copies, optimiser tables and state).  Before a
+        replay: (i) optimiser tables that were rebuilt, or modules that were moved / cast, invalidate the graph -> loud
+        error; (ii) weights that were overwritten in place since (load_state_dict of a checkpoint, src/cgan.py:511-542) only
+        leave the packed bf16 copies stale -> they are re-packed here, into the same buffers."""
+        sig = self._state_signature()
+        if sig == self._capture_state:
+            return
+        if sig[:3] != self._capture_state[:3]:
+            raise RuntimeError("the optimiser tables or the module runtimes changed since capture() (set_packed_grads / "
+                               "load of a state with a different layout / .to()): call capture() again")
+        for r in self.rt.values():
+            r.ensure_packed()
+        self._capture_state = self._state_signature()
 
     def release_graphs(self):
         """Drop the captured graphs (and the NCCL work they may hold) -- call before destroy_process_group()."""
-        torch.cuda.synchronize()
+        if self._graphs:
+            torch.cuda.synchronize(self.device)
         self._graphs, self._graph = [], None
 
     def replay(self, x=None, m=None, y=None):
         """Run the captured step (optionally on new inputs of the captured shape)."""
         if not self._graph:
             raise RuntimeError("call capture() first")
+        # lr / grad_scale live in a device vector the captured Adam kernels read through a pointer: push scheduler changes
+        # (ExponentialLR once per epoch, src/cgan.py:383-384) before the launch
+        self.optim_D.sync_hyper(); self.optim_G.sync_hyper()
+        self._validate_capture()
         for dst, src in zip(self._static, (x, m, y)):
             if src is not None:
                 dst.copy_(src, non_blocking=True)
-        pending = []
-        for g, req in self._graphs:
+        if self._graph == "eager":
+            return self.train_step(*self._static)
+        for g in self._graphs:
             g.replay()
-            if req is not None:
-                self._reduce(req, pending)
         self.optim_D.bump_host_counters(); self.optim_G.bump_host_counters()
         return self.losses
 
@@ -457,7 +604,8 @@ class STCGANEngine:
         d = dict(zip(SLOTS, v))
         c = self.cfg
         d["D_loss"] = c.lambda2 * d["D1_loss"] + c.lambda3 * d["D2_loss"]
-        d["G_loss"] = d["data1_loss"] + c.lambda1 * d["data2_loss"] + c.lambda2 * d["G1_loss"] + c.lambda3 * d["G2_loss"]
+        d["G_loss"] = (d["data1_loss"] + c.lambda1 * d["data2_loss"] + c.lambda2 * d["G1_loss"] + c.lambda3 * d["G2_loss"]
+                       + c.lambda4 * d["vis1_loss"] + c.lambda5 * d["vis2_loss"])
         return d
 
 

@@ -58,15 +58,16 @@ def _nhwc(t: torch.Tensor):
 
 
 SPLITK_MAX_ELEMS = 4 * 1024 * 1024     # only small outputs (bottleneck layers) get a split-K workspace
-_SPLITK_WS = {}                        # (elements, device, lane) -> zeroed fp32 workspace (kept zero by the finisher)
-_CONCURRENT_STREAMS = set()            # raw handles of streams that run next to the caller's main stream (engine lanes)
+# (elements, device, raw stream handle) -> zeroed fp32 workspace (kept all-zero between calls by the finisher kernel).
+# Keyed by the ACTUAL stream of the call: two streams -- engine lanes, a user's inference stream next to a training step, a
+# second engine -- can never `red.add` into / clear the same buffer under each other.  The buffers are small (<= 16 MB, a few
+# sizes per stream) and live for the life of the process.
+_SPLITK_WS = {}
 
 
 def register_concurrent_stream(stream):
-    """Tell the library that `stream` runs concurrently with other streams of the same step: work issued on it gets its own
-    persistent scratch (everything else -- the default stream, a warm-up stream, a capture stream -- shares the "main" one,
-    since those never run at the same time)."""
-    _CONCURRENT_STREAMS.add(stream.cuda_stream)
+    """Kept for callers of the round-1 API: split-K scratch is now always per stream, nothing to register."""
+    return None
 
 
 def tc_eligible_conv(k: int, nout: int) -> bool:
@@ -102,8 +103,7 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
     if backend == BACKEND_TC and n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
         # split-K partial sums: one persistent, self-cleaning (all-zero between calls) workspace per size and stream --
         # no allocation and no memset launch per convolution; concurrent streams never share one
-        cur = torch.cuda.current_stream().cuda_stream
-        key = (n * oh * ow * nout, x.device.index, cur if cur in _CONCURRENT_STREAMS else 0)
+        key = (n * oh * ow * nout, x.device.index, torch.cuda.current_stream().cuda_stream)
         wst = _SPLITK_WS.get(key)
         if wst is None:
             wst = _SPLITK_WS[key] = torch.zeros(key[0], dtype=torch.float32, device=x.device)

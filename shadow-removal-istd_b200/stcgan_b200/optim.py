@@ -28,6 +28,10 @@ class FusedAdam(torch.optim.Optimizer):
         self._pack_targets = {}  # id(param) -> ConvOp whose bf16 packed copies the Adam kernel refreshes in the same pass
         self.grad_scale = 1.0
         self._order_key = None   # optional: parameter -> sort key of its blocks in the device table (see set_block_order)
+        # Every (re)build of a device table bumps `generation`.  A captured CUDA graph bakes in the addresses of the table,
+        # the block list, the hyper-parameter vector and the exp_avg / exp_avg_sq tensors, so whoever captured `step()`
+        # records the generation and must not replay the graph after it changed (STCGANEngine.replay checks this).
+        self.generation = 0
 
     def set_packed_grads(self, views):
         """Engine hook: gradients that live in packed [16][d0][d1] layout instead of `p.grad`."""
@@ -47,8 +51,41 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables.clear()
 
     def load_state_dict(self, state_dict):
+        """torch.optim.Optimizer.load_state_dict, but state that already lives on the device is updated IN PLACE: the
+        exp_avg / exp_avg_sq tensors (and with them the device tables that point at them) keep their addresses, so a
+        checkpoint (src/cgan.py:511-523) can be restored after the train step was captured into a CUDA graph.  The device
+        step counter / bias corrections are refreshed from the loaded `step`."""
+        old = {p: dict(st) for p, st in self.state.items() if "exp_avg" in st}
         super().load_state_dict(state_dict)
-        self._tables.clear()
+        kept = True
+        for p, st_old in old.items():
+            st = self.state.get(p)
+            if st is None or "exp_avg" not in st:
+                kept = False
+                continue
+            for k in ("exp_avg", "exp_avg_sq"):
+                if st[k].shape == st_old[k].shape and st_old[k].dtype == torch.float32:
+                    st_old[k].copy_(st[k])
+                    st[k] = st_old[k]
+                else:
+                    kept = False
+            st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32)
+        if not kept or not old:
+            self._tables.clear()
+            return
+        for gi, group in enumerate(self.param_groups):
+            t = self._tables.get(gi)
+            if t is None:
+                continue
+            if t["sig"] != self._signature(group):
+                self._tables.pop(gi)
+                continue
+            t["keep"] = [(p, g, self.state[p]) for p, g, _ in t["keep"]]      # the state dicts are new objects
+            b1, b2 = group["betas"]
+            steps_done = float(t["keep"][0][2]["step"])
+            t["hyper_host"] = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(self.grad_scale),
+                               steps_done, 0.0, 0.0]
+            t["hyper"].copy_(torch.tensor(t["hyper_host"], dtype=torch.float32))
 
     def _state_for(self, p):
         st = self.state[p]
@@ -135,6 +172,17 @@ class FusedAdam(torch.optim.Optimizer):
             t = self._tables.get(gi)
             if t is None or t["sig"] != self._signature(group):
                 self._tables[gi] = self._build_table(group)
+                self.generation += 1
+
+    def sync_hyper(self):
+        """Push lr / grad_scale of every param group to the device vector the kernels read (a plain H2D copy outside any
+        graph: the vector is read through its pointer, so a captured `step()` picks the new values up on its next replay).
+        STCGANEngine.replay calls this before every replay -- the per-epoch ExponentialLR of src/cgan.py:383-384 then acts on
+        the captured path exactly as on the eager one."""
+        for gi, group in enumerate(self.param_groups):
+            t = self._tables.get(gi)
+            if t is not None:
+                self._sync_hyper(group, t)
 
     def bump_host_counters(self):
         """Account on the host for one device-side step (used after a CUDA-graph replay of `step`)."""
@@ -166,12 +214,20 @@ class FusedAdam(torch.optim.Optimizer):
                                               t["hyper"].data_ptr(), int(tick), int(max_ctas),
                                               torch.cuda.current_stream().cuda_stream),
                    "stcgan_adam_step_range")
-        if last:
-            for p, _, st in t["keep"]:
-                st["step"] += 1
+        # host bookkeeping for the tensors of THIS launch: version bump (whoever caches derived copies -- the thin layers'
+        # packed weights -- re-derives them on next use) and "p1 / p2 are fresh" for the tensors the kernel re-packed itself
+        ids = {id(p) for p in params}
+        for p, _, _ in t["keep"]:
+            if id(p) in ids:
                 torch.autograd.graph.increment_version(p)
-            for conv in t["fused"]:
+        for conv in t["fused"]:
+            if id(conv.weight) in ids:
                 conv.mark_packed()
+        # (during graph capture no kernel runs: the host step counter must not advance -- it would run ahead of the device
+        # counter hyper[5])
+        if last and not torch.cuda.is_current_stream_capturing():
+            for _, _, st in t["keep"]:
+                st["step"] += 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -189,8 +245,10 @@ class FusedAdam(torch.optim.Optimizer):
             _lib.check(lib.stcgan_adam_step(t["table"].data_ptr(), t["blocks"].data_ptr(), t["nblocks"],
                                             t["hyper"].data_ptr(), torch.cuda.current_stream().cuda_stream),
                        "stcgan_adam_step")
+            counting = not torch.cuda.is_current_stream_capturing()      # see step_partial
             for p, _, st in t["keep"]:
-                st["step"] += 1
+                if counting:
+                    st["step"] += 1
                 torch.autograd.graph.increment_version(p)
             for conv in t["fused"]:
                 conv.mark_packed()          # the kernel above already rewrote conv.p1 / conv.p2

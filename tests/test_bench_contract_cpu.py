@@ -32,11 +32,17 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["dtype"] == "f32"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the stated configuration, not a sample of it: the full 16-image batch per step, --steps / --warmup honoured
+    assert d["steps"] == 1 and d["warmup"] == 1 and d["config"]["global_batch"] == 16 and "full 16-image" in cb["sample"]
+    assert abs(d["ms_per_step"] * d["value"] / 1e3 - 16) < 1e-6
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
 
 
 def test_last_b200_bench_line_has_every_contract_key():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_v*.json")), key=lambda f: int(f.rsplit("_v", 1)[1].split(".")[0]))
+    def order(f):
+        b = os.path.basename(f)
+        return int(b[1:3]), int(b.rsplit("_v", 1)[1].split(".")[0])
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_v*.json")), key=order)
     assert files, "no committed B200 bench line under profiles/"
     d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
     _check_common(d)

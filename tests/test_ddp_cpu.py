@@ -83,6 +83,26 @@ def _worker(rank, world, port, out_dir):
     O.cal_loss(O.discriminator_forward(s, inp, training=True), 1.0).backward()
     glob = torch.cat([s[k].grad.reshape(-1) for k in keys])
     assert (glob - ref_flat).norm() / ref_flat.norm() > 1e-3
+    # ---- 3. the engine's D-phase protocol since round 2: D1's bucket first (blocking on its own lane), then D2's
+    bufs.update({"D1": torch.ones(4) * (rank + 1), "D2": torch.ones(4) * 2 * (rank + 1)})
+    sync.log.clear(); pending = []
+    sync.reduce(("D1",), True, pending)
+    sync.reduce(("D2",), True, pending)
+    assert not pending and torch.equal(bufs["D1"], torch.ones(4) * 3) and torch.equal(bufs["D2"], torch.ones(4) * 6)
+    assert sync.log == [(("D1",), True), (("D2",), True)]
+
+    # ---- 4. the single-process data-parallel oracle used by the 2-GPU parity test (tests/test_ddp_gpu.py) states the same
+    # thing as real ranks: D-phase gradients of O.OracleDataParallel == all-reduced per-rank gradients / world
+    torch.manual_seed(7)
+    st = O.build_all_states(ngf=8, ndf=8)
+    shards = [tuple(t.double() for t in O.make_istd_batch(1, 256, 256, seed=40 + r)) for r in range(world)]
+    mine = O.OracleTrainer(st, dtype=torch.float64).train_step(*shards[rank], do_optim=False, keep_grads=True)
+    flat = torch.cat([g.reshape(-1) for n in ("D1", "D2") for g in mine["grads_D"][n]])
+    dist.all_reduce(flat)
+    flat /= world
+    _, g = O.OracleDataParallel(st, world, dtype=torch.float64).train_step(shards)
+    want = torch.cat([t.reshape(-1) for n in ("D1", "D2") for t in g[n]])
+    assert torch.allclose(flat, want, rtol=1e-9, atol=1e-12), float((flat - want).abs().max())
     with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
         f.write("ok")
     dist.destroy_process_group()

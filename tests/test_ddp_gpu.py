@@ -1,0 +1,132 @@
+"""Multi-rank parity on real GPUs: two NCCL ranks, each with its own shard, against the
+single-process data-parallel oracle `O.OracleDataParallel` (every shard through its OWN forward -- rank-local BatchNorm
+statistics, nn.DataParallel's per-replica semantics of src/cgan.py:78-84 -- gradients averaged, one Adam update).
+
+Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on a single-GPU box.  Both execution modes are covered: the eager step
+(all-reduces issued inline on c10d's stream) and the captured step (the collectives are part of the ONE CUDA graph).
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mode, out_dir):
+    for p in (os.path.join(ROOT, "shadow-removal-istd_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import stcgan_b200 as S
+    import stcgan_oracle as O
+    from stcgan_b200 import ops
+    from conftest import rel_err
+
+    states = O.build_all_states()
+    B = 2
+    shards = [O.make_istd_batch(B, 256, 256, seed=300 + r) for r in range(world)]
+
+    def build():
+        nets = dict(G1=S.UnetGenerator(3, 1, precision=mode), G2=S.UnetGenerator(4, 3, precision=mode),
+                    D1=S.NLayerDiscriminator(4, precision=mode), D2=S.NLayerDiscriminator(7, precision=mode))
+        for n, mod in nets.items():
+            mod.load_state_dict(states[n]); mod.to(dev).train()
+        eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"], S.TrainConfig(), process_group=dist.group.WORLD)
+        return nets, eng
+
+    def grads(eng, nets, n):
+        out = []
+        for p in nets[n].parameters():
+            v, d0, d1 = eng.rt[n].param_grad_views[id(p)]
+            out.append((ops.unpack_grad(v, d0, d1) if d0 else v.view(p.shape).clone()) / world)   # the buffers hold the SUM
+        return out
+
+    def flat_params(nets):
+        return torch.cat([p.detach().reshape(-1) for n in nets.values() for p in n.parameters()])
+
+    x, m, y = (t.to(dev) for t in shards[rank])
+    # ---- eager step --------------------------------------------------------------------------------------------------
+    nets, eng = build()
+    eng.train_step(x, m, y)
+    torch.cuda.synchronize()
+    assert [names for names, _ in eng.sync.log[:2]] == [("D1",), ("D2",)]       # D1's bucket goes first, on its own lane
+    mine = flat_params(nets)
+    ref0 = mine.clone(); dist.broadcast(ref0, 0)
+    assert torch.equal(mine, ref0), "replicas diverged after the eager step"
+    tight = mode == "fp32"
+    if rank == 0:
+        dp = O.OracleDataParallel(states, world, O.HyperParams(), dtype=torch.float64)
+        outs, g = dp.train_step([tuple(t.double() for t in s) for s in shards])
+        L = eng.loss_dict()
+        tol = 1e-3 if tight else 2e-2
+        for k in ("D1_loss", "D2_loss", "data1_loss", "data2_loss"):
+            assert abs(L[k] - float(outs[0][k])) <= tol * abs(float(outs[0][k])), (k, L[k], float(outs[0][k]))
+        assert rel_err(eng.last["m_pred"], outs[0]["m_pred"]) < tol and rel_err(eng.last["y_pred"], outs[0]["y_pred"]) < tol
+        worst = 0.0
+        for n in ("D1", "D2"):
+            for p, got, want in zip(nets[n].parameters(), grads(eng, nets, n), g[n]):
+                e = rel_err(got, want)
+                worst = max(worst, e)
+                assert e < (5e-3 if tight else 0.35), (n, tuple(p.shape), e)
+        # ...and they are NOT the gradients of shard 0 alone (the exchange really happened)
+        solo = O.OracleTrainer(states, O.HyperParams(), dtype=torch.float64).train_step(
+            *(t.double() for t in shards[0]), keep_grads=True)
+        far = rel_err(torch.cat([t.reshape(-1) for t in grads(eng, nets, "D1")]),
+                      torch.cat([t.reshape(-1) for t in solo["grads_D"]["D1"]]))
+        assert far > 10 * max(worst, 1e-3), (far, worst)
+        # update direction of every network vs the data-parallel oracle's single Adam step
+        for n in nets:
+            agree = total = 0
+            for (k, p), q in zip(nets[n].named_parameters(), dp.t.params[n]):
+                dm_ = p.detach().cpu().double() - states[n][k].double(); dr = q.detach() - states[n][k].double()
+                agree += int((torch.sign(dm_) == torch.sign(dr)).sum()); total += dm_.numel()
+            assert agree / total > (0.98 if tight else 0.8), (n, agree / total)
+        print(f"[ddp {mode}] eager: worst D-gradient error vs data-parallel oracle {worst:.3e}; vs shard-0-only {far:.3e}", flush=True)
+    eng.release_graphs()
+    del eng, nets
+    # ---- captured step: one eager warm-up + 2 replays == three eager steps ------------------------------------------------
+    nets_a, a = build()
+    for _ in range(3):
+        a.train_step(x, m, y)
+    nets_b, b = build()
+    b.capture(x, m, y, warmup=1)
+    assert len(b._graphs) == 1 and b._graph == "graph"
+    for _ in range(2):
+        b.replay()
+    torch.cuda.synchronize()
+    pb = flat_params(nets_b)
+    ref0 = pb.clone(); dist.broadcast(ref0, 0)
+    assert torch.equal(pb, ref0), "replicas diverged after graph replays"
+    la, lb = a.losses.cpu(), b.losses.cpu()
+    assert (la[:6] - lb[:6]).abs().max().item() <= (2e-3 if tight else 2e-2) * la[:6].abs().max().item(), (la, lb)
+    d = (flat_params(nets_a) - pb).abs()
+    assert d.max().item() <= 2 * 5e-4 * 3 * 1.01 and (d > 0.5 * 1e-4).float().mean().item() < 0.05
+    a.release_graphs(); b.release_graphs()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write("ok")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_two_rank_nccl_step_vs_data_parallel_oracle(tmp_path, mode):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), mode, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))

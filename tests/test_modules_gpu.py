@@ -24,15 +24,22 @@ def _cast_state(sd, dtype):
     return {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
 
 
-def _oracle_grads(kind, sd, x, dout, dtype, training=True):
+def _oracle_grads(kind, sd, x, dout, dtype, training=True, emulate=None):
+    """`emulate=torch.bfloat16`: the same restatement with every convolution's operands, output and incoming gradient rounded
+    to bf16 (O.emulate_conv_precision) -- the rounding-noise yardstick for the bf16 mode's end-to-end gradients."""
     sd = _cast_state(sd, dtype)
     keys = O.trainable_keys(sd)
     for k in keys:
         sd[k].requires_grad_(True)
     xi = x.to(dtype).requires_grad_(True)
     fn = O.generator_forward if kind == "G" else O.discriminator_forward
-    out = fn(sd, xi, training=training)
-    out.backward(dout.to(dtype))
+    if emulate is not None:
+        with O.emulate_conv_precision(emulate):
+            out = fn(sd, xi, training=training)
+            out.backward(dout.to(dtype))
+    else:
+        out = fn(sd, xi, training=training)
+        out.backward(dout.to(dtype))
     return out.detach(), xi.grad, {k: sd[k].grad for k in keys}, sd
 
 
@@ -64,7 +71,10 @@ def test_forward_backward_vs_oracle(cuda, lib, states, mode, net):
     out.backward(dout.to(cuda))
     torch.cuda.synchronize()
     o64, dx64, g64, sd64 = _oracle_grads(net[0], states[net], inp, dout, torch.float64)
-    o32, dx32, g32, sd32 = _oracle_grads(net[0], states[net], inp, dout, torch.float32)
+    if mode == "fp32":
+        o32, dx32, g32, sd32 = _oracle_grads(net[0], states[net], inp, dout, torch.float32)
+    else:       # yardstick of the bf16 mode: the float64 oracle with bf16-rounded convolution operands / gradients
+        o32, dx32, g32, sd32 = _oracle_grads(net[0], states[net], inp, dout, torch.float64, emulate=torch.bfloat16)
     tol = OUT_TOL[mode]
     assert rel_err(out, o64) < tol, f"output rel err {rel_err(out, o64):.3e}"
     # BN buffers after one training forward
@@ -78,11 +88,13 @@ def test_forward_backward_vs_oracle(cuda, lib, states, mode, net):
         noise = rel_err(g32[k], g64[k])
         e = rel_err(p.grad, g64[k])
         worst = max(worst, e)
-        bound = max(5e-3, 2 * noise) if mode == "fp32" else 0.5
-        assert e < bound, f"{k}: grad rel err {e:.3e} (fp32-vs-fp64 oracle noise {noise:.3e})"
+        # fp32 mode: 2 x the reference's own fp32-vs-fp64 noise; bf16 mode: 1.5 x the error of the bf16-emulating oracle
+        # (a kernel that drops or mis-scales a term exceeds the rounding noise of a correct bf16 pipeline)
+        bound = max(5e-3, 2 * noise) if mode == "fp32" else 1.5 * max(noise, 2e-2)
+        assert e < bound, f"{k}: grad rel err {e:.3e} (yardstick {noise:.3e})"
         assert _cos(p.grad, g64[k]) > (0.9999 if mode == "fp32" else 0.85), k
     e = rel_err(xi.grad, dx64)
-    assert e < (max(5e-3, 2 * rel_err(dx32, dx64)) if mode == "fp32" else 0.5), f"input grad {e:.3e}"
+    assert e < (max(5e-3, 2 * rel_err(dx32, dx64)) if mode == "fp32" else 1.5 * max(rel_err(dx32, dx64), 2e-2)), f"input grad {e:.3e}"
     print(f"{net} {mode}: out {rel_err(out, o64):.2e}  worst param-grad {worst:.2e}  dx {e:.2e}")
 
 

@@ -37,6 +37,10 @@ def test_engine_train_step_vs_oracle(cuda, lib, states, mode):
     x, m, y = O.make_istd_batch(2, 256, 256, seed=42)
     ref = O.OracleTrainer(states, O.HyperParams(), dtype=torch.float64)
     r = ref.train_step(x.double(), m.double(), y.double(), keep_grads=True)
+    if mode == "bf16":      # rounding-noise yardstick: the same oracle with bf16-rounded convolution operands / gradients
+        with O.emulate_conv_precision(torch.bfloat16):
+            emu = O.OracleTrainer(states, O.HyperParams(), dtype=torch.float64).train_step(
+                x.double(), m.double(), y.double(), keep_grads=True)
     eng.train_step(x.to(cuda), m.to(cuda), y.to(cuda))
     torch.cuda.synchronize()
     L = eng.loss_dict()
@@ -51,11 +55,12 @@ def test_engine_train_step_vs_oracle(cuda, lib, states, mode):
     from stcgan_b200 import ops
     for n in ("D1", "D2"):
         rt = eng.rt[n]
-        for p, gref in zip(nets[n].parameters(), r["grads_D"][n]):
+        for i, (p, gref) in enumerate(zip(nets[n].parameters(), r["grads_D"][n])):
             v, d0, d1 = rt.param_grad_views[id(p)]
             got = ops.unpack_grad(v, d0, d1) if d0 else v.view(p.shape)
             e = rel_err(got, gref)
-            assert e < (5e-3 if mode == "fp32" else 0.5), (n, tuple(p.shape), e)
+            bound = 5e-3 if mode == "fp32" else 1.5 * max(rel_err(emu["grads_D"][n][i], gref), 2e-2)
+            assert e < bound, (n, tuple(p.shape), e, bound)
     # BN running statistics: D saw 4 training forwards, G one (cgan.py:281-289, 321-324)
     for n in nets:
         for k, v in nets[n].state_dict().items():
@@ -119,20 +124,6 @@ def test_engine_matches_autograd_modules(cuda, lib, states):
             assert d.max().item() <= 2.02 * lr and (d > 0.1 * lr).float().mean().item() < 0.02, (n, k)
 
 
-def test_cuda_graph_replay_equals_eager(cuda, lib, states):
-    import stcgan_b200 as S
-    x, m, y = (t.to(cuda) for t in O.make_istd_batch(2, 256, 256, seed=11))
-    a = _build("bf16", cuda, states)
-    eng = S.STCGANEngine(a["G1"], a["G2"], a["D1"], a["D2"])
-    eng.capture(x, m, y, warmup=1)
-    l1 = eng.replay(x, m, y).clone(); l2 = eng.replay(x, m, y).clone()
-    torch.cuda.synchronize()
-    assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and not torch.equal(l1, l2)   # weights moved
-    assert eng.graph_launches > 300
-    st = eng.optim_G.state_dict()["state"][0]
-    assert float(st["step"]) == 4       # 1 warm-up + capture + 2 replays
-
-
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_inference_and_quantisation_vs_oracle(cuda, lib, states, mode, golden):
     """configs[3] geometry (480x640, eval BN) at batch 1 + the uint8 contract of utils.float2uint."""
@@ -185,7 +176,7 @@ def test_replay_async_pipelines_inputs_and_loss_reads(cuda, lib, states):
     import stcgan_b200 as S
     nets = _build("bf16", cuda, states)
     eng = S.STCGANEngine(nets["G1"], nets["G2"], nets["D1"], nets["D2"])
-    batches = [tuple(t.contiguous().pin_memory() for t in O.make_istd_batch(2, 64, 64, seed=s)) for s in (1, 2, 3)]
+    batches = [tuple(t.contiguous().pin_memory() for t in O.make_istd_batch(2, 256, 256, seed=s)) for s in (1, 2, 3)]
     eng.capture(*(t.to(cuda) for t in batches[0]), warmup=1)
     assert eng.replay_async(*batches[0]) is None
     l0 = eng.replay_async(*batches[1])                   # losses of the step on batches[0]
@@ -196,4 +187,4 @@ def test_replay_async_pipelines_inputs_and_loss_reads(cuda, lib, states):
         assert l is not None and not l.is_cuda and torch.isfinite(l).all()
     assert torch.equal(l2, eng.losses.cpu())             # the last step's losses are what the device holds
     assert not torch.equal(l0, l1) and not torch.equal(l1, l2)
-    assert float(eng.optim_G.state_dict()["state"][0]["step"]) == 5     # 1 warm-up + capture + 3 replays
+    assert float(eng.optim_G.state_dict()["state"][0]["step"]) == 4     # 1 warm-up + 3 replays (capturing is not a step)
