@@ -180,6 +180,13 @@ int stcgan_bn_stats(int dtype, const void* y, int64_t P, int C, int ld, double* 
 int stcgan_bn_finalize(const double* acc, int64_t P, int C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int training,
                        float* mean_invstd, float* scale_shift, void* stream);
+/* the running-statistics half of the training-mode call above, on its own (nn.BatchNorm2d's momentum update,
+ * src/models/stcgan_d.py:36,45): statistics = sum over the STCGAN_BN_SLOTS slots of acc[slot][2][C] over `count` values per
+ * channel; running_mean / running_var <- (1 - momentum) * old + momentum * (mean / unbiased variance).  Used after a forward
+ * pass that ran stcgan_bn_fused_apply with running_mean == NULL, so that two forward passes of one network (cgan.py:321-324:
+ * D(real) and D(fake)) can execute concurrently while the updates still land in the reference's order. */
+int stcgan_bn_running_update(const double* acc, int64_t count, int C, float* running_mean, float* running_var,
+                             float momentum, void* stream);
 /* out1 = act1(y*scale + shift) (and optionally out2 = act2(..)) over the cropped region [N, HC, WC] of
  * y [N, H, W, C]; scale_shift == NULL means identity (layers without BatchNorm).  out2 may be NULL. */
 int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,

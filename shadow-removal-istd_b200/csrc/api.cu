@@ -34,6 +34,7 @@ int pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void
 int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st);
 int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float momentum, float eps, int training, float* mean_invstd, float* scale_shift, cudaStream_t st);
+int bn_running_update(const double* acc, long long count, int C, float* rmean, float* rvar, float momentum, cudaStream_t st);
 int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, int HC, int WC,
                  void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st);
 int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
@@ -167,6 +168,12 @@ int stcgan_bn_finalize(const double* acc, int64_t P, int C, const float* gamma, 
   STCGAN_REQUIRE(C > 0 && gamma && beta && mean_invstd && scale_shift && (acc || !training) && (P > 0 || !training));
   return bn_finalize(acc, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, mean_invstd,
                      scale_shift, as_stream(stream));
+}
+
+int stcgan_bn_running_update(const double* acc, int64_t count, int C, float* running_mean, float* running_var, float momentum,
+                             void* stream) {
+  STCGAN_REQUIRE(acc && count > 0 && C > 0 && running_mean && running_var);
+  return bn_running_update(acc, count, C, running_mean, running_var, momentum, as_stream(stream));
 }
 
 int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,

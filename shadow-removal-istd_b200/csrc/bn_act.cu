@@ -187,6 +187,33 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, long long P, 
   scale_shift[c] = sc; scale_shift[C + c] = beta[c] - mean * sc;
 }
 
+// deferred running-statistics update: the momentum update that bn_fused_apply_kernel's block 0 performs, as a launch of
+// its own (same arithmetic, bit for bit: sums over the statistic slots in fp64, 1/count and count/(count-1) from the
+// host).  Lets two training forward passes of one network run concurrently -- the second one skips its update and
+// applies it afterwards, which keeps the reference's update ORDER (the exponential average does not commute).
+__global__ void bn_running_update_kernel(const double* __restrict__ acc, int C, double inv_count, double unbias,
+                                         float* __restrict__ rmean, float* __restrict__ rvar, float momentum) {
+  pdl_prologue();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+#pragma unroll
+  for (int k = 0; k < STCGAN_BN_SLOTS; ++k) { s += acc[(2 * k) * C + c]; q += acc[(2 * k + 1) * C + c]; }
+  const double m = s * inv_count;
+  double var = q * inv_count - m * m;
+  if (var < 0.0) var = 0.0;
+  const double unbiased = var * unbias;
+  rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+  rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+}
+
+int bn_running_update(const double* acc, long long count, int C, float* rmean, float* rvar, float momentum, cudaStream_t st) {
+  const double inv_count = count > 0 ? 1.0 / (double)count : 0.0;
+  const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+  launch_k(bn_running_update_kernel, (C + 127) / 128, 128, 0, st, acc, C, inv_count, unbias, rmean, rvar, momentum);
+  return finish_launch();
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward apply (+ activation, optional second output with another activation, optional crop)
 // ---------------------------------------------------------------------------------------------

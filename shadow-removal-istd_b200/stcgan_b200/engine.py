@@ -364,10 +364,22 @@ class STCGANEngine:
         self.optim_D.step_partial(d2_params, tick=False, last=True)           # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
-        c2r_g = None
-        if cfg.rel or not cfg.skip_dead_real_passes:
-            c2r_g, _ = rt["D2"].forward([x, m, y], True, packed=pk_xmy)          # cgan.py:323 (SGAN: running stats only)
-        c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)           # cgan.py:324
+        # D2's two forward passes with the updated discriminator (cgan.py:323-324) sit on the step's critical path.  They are
+        # independent except for the ORDER of their BatchNorm running-statistics updates (real first), so the real pass runs
+        # on a lane next to the fake pass, whose updates are deferred and applied after the join (same arithmetic, same order)
+        c2r_g, overlap_real = None, bool(L.streams) and os.environ.get("STCGAN_OVERLAP_REAL", "1") != "0"
+        need_real = cfg.rel or not cfg.skip_dead_real_passes
+        if need_real and overlap_real:
+            L.lane_wait(1)
+            with L.lane(1):
+                c2r_g, _ = rt["D2"].forward([x, m, y], True, packed=pk_xmy)      # cgan.py:323 (SGAN: running stats only)
+            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp, defer_running=True)   # cgan.py:324
+            L.join_lanes((1,))
+            rt["D2"].apply_deferred_running(w2f)
+        else:
+            if need_real:
+                c2r_g, _ = rt["D2"].forward([x, m, y], True, packed=pk_xmy)
+            c2f, w2f = rt["D2"].forward([x, mp, yp], True, packed=pk_xmpyp)
         L.join()                                                                  # D1's G-phase passes (lane 2)
         dm, dy = newg(mp), newg(yp)
         terms = [dict(kind=ops.KIND_L1, a=mp, b=m, grad=dm, weight=1.0, loss_weight=1.0, slot=4),
@@ -397,33 +409,39 @@ class STCGANEngine:
             ops.unpack_input_grad(dig2, 3, 1, dm, True)       # G2's input gradient, mask channel (cgan.py:286)
         if multi:
             yield ("G2",), False                              # async: overlaps G1's backward
-        # G1's backward in two halves: after the decoder half its up-conv weight gradients (64 % of G1's parameters) are
-        # final and go on the wire under the encoder half; by then G2's sum has landed, so G2's share of optim_G.step
-        # (cgan.py:351; an HBM-bound stream over 28 B/parameter) runs on a lane underneath the encoder half as well
-        with self._critical():
-            rt["G1"].backward(wg1, dm, False, part="dec")
-        if multi:
-            yield ("G1.ups",), False, ("G2",)
+        # G1's backward in two halves.  optim_G.step (cgan.py:351; an HBM-bound stream over 28 B/parameter) is applied per
+        # gradient bucket on a lane underneath it: G2's share as soon as G2's (summed) gradients are there, i.e. under the
+        # decoder half; after the decoder half G1's up-conv weight gradients (64 % of its parameters) are final, go on the
+        # wire and are applied under the encoder half; only the rest of G1 (19.5 M parameters) is updated after the backward
         split = bool(L.streams)
+        cap = int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148"))
+        g2_params = list(self.nets["G2"].parameters())
         if split:
             L.fork()
             with L.lane(0):
-                self.optim_G.step_partial(list(self.nets["G2"].parameters()), tick=True, last=False,
-                                          max_ctas=int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148")))
+                if multi:
+                    yield (), False, ("G2",)                  # this lane (not the backward chain) waits for G2's sum
+                self.optim_G.step_partial(g2_params, tick=True, last=False, max_ctas=cap)
+        with self._critical():
+            rt["G1"].backward(wg1, dm, False, part="dec")
+        if multi:
+            yield ("G1.ups",), False
+        if split:
+            L.lane_wait(0)                                    # the lane sees the decoder half's weight gradients
+            with L.lane(0):
+                if multi:
+                    yield (), False, ("G1.ups",)
+                self.optim_G.step_partial(self._g1_ups, tick=False, last=False, max_ctas=cap)
         with self._critical():
             rt["G1"].backward(wg1, dm, False, part="enc")
         if split:
             L.join()
-        if multi:
-            yield ("G1.rest",), False, ("G1.ups",)            # the last bucket goes on the wire ...
-        if split:
-            self.optim_G.step_partial(self._g1_ups, tick=False, last=False)      # ... under the update of the bucket before it
             if multi:
-                yield (), True
+                yield ("G1.rest",), True
             self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
         else:
             if multi:
-                yield (), True
+                yield ("G1.ups", "G1.rest"), True            # (blocking: waits for G2's sum as well)
             self.optim_G.step()                               # cgan.py:351
         for r in rt.values():
             r.ensure_packed()                                 # re-pack the updated weights for the next step

@@ -163,9 +163,11 @@ class BNOp:
         self.ggamma = self.gbeta = None     # fp32 gradient views
         self.shared_counter = False         # True: num_batches_tracked is a view into the runtime's flat counter tensor
 
-    def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE, stats_done=False):
+    def forward(self, y, scratch, training, out1, act1, out2=None, act2=ACT_NONE, stats_done=False, deferred=None):
         """[stats (training, unless the producing GEMM already accumulated them: stats_done)] -> finalize + apply in one
-        launch.  scratch: dict with 'acc' (f64 [BN_SLOTS,2,C], zeroed), 'mi', 'ss' (f32 [2,C])."""
+        launch.  scratch: dict with 'acc' (f64 [BN_SLOTS,2,C], zeroed), 'mi', 'ss' (f32 [2,C]).
+        `deferred` (a list): the running-statistics update is NOT performed; (self, acc, count) is appended instead and
+        `apply_running_update` performs it later (the caller orders it after a concurrently running pass)."""
         m = self.m
         n, h, w, _ = y.shape
         if training:
@@ -174,15 +176,24 @@ class BNOp:
             if not stats_done:
                 ops.bn_stats(y, scratch["acc"])          # fills slot 0
             use_running = m.track_running_stats and m.running_mean is not None
+            now = use_running and deferred is None
             ops.bn_fused_apply(y, scratch["acc"], n * h * w, m.weight.detach(), m.bias.detach(),
-                               m.running_mean if use_running else None, m.running_var if use_running else None,
+                               m.running_mean if now else None, m.running_var if now else None,
                                BN_MOMENTUM if m.momentum is None else m.momentum, m.eps, True, scratch["mi"], scratch["ss"],
                                out1, act1, out2, act2)
-            if use_running and m.num_batches_tracked is not None and not self.shared_counter:
+            if use_running and deferred is not None:
+                deferred.append((self, scratch["acc"], n * h * w))
+            if use_running and m.num_batches_tracked is not None and not self.shared_counter and deferred is None:
                 m.num_batches_tracked.add_(1)
         else:
             ops.bn_fused_apply(y, None, n * h * w, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var,
                                0.0, m.eps, False, scratch["mi"], scratch["ss"], out1, act1, out2, act2)
+
+    def apply_running_update(self, acc, count):
+        m = self.m
+        ops.bn_running_update(acc, count, m.running_mean, m.running_var, BN_MOMENTUM if m.momentum is None else m.momentum)
+        if m.num_batches_tracked is not None and not self.shared_counter:
+            m.num_batches_tracked.add_(1)
 
     def backward(self, y, scratch, training, g1, act1, g2, act2, dy, want_param_grads, zero_acc=True):
         if zero_acc:
@@ -526,18 +537,21 @@ class DiscriminatorRuntime(_NetRuntimeBase):
         self.use_sigmoid = use_sigmoid
         super().__init__(list(convs), [b for b in bns if b is not None], precision)
 
-    def forward(self, sources, training, packed=None):
+    def forward(self, sources, training, packed=None, defer_running=False):
+        """`defer_running` (training only): BatchNorm running statistics are left untouched; the workspace records the pending
+        updates and `apply_deferred_running(ws)` performs them -- see BNOp.forward."""
         self.ensure_packed()
         dt, dev = self.act_dtype, self.device()
         n, _, h, w = sources[0].shape
         inp, inp_b = self._packed_input(sources, packed)
         thin_in = inp_b is not None
         nl = len(self.layers)
+        deferred = [] if (defer_running and training) else None
         arena = _BNArena([b.c for b in self.bns], dev)
-        if training and self.counters is not None:
+        if training and self.counters is not None and deferred is None:      # (a deferred pass counts when its updates land)
             self.counters.add_(1)
         ws = {"inp": inp, "inp_b": inp_b, "n": n, "training": training, "arena": arena, "y": [None] * nl, "a": [None] * nl,
-              "bn": [None] * nl, "s": [(h, w)]}
+              "bn": [None] * nl, "s": [(h, w)], "deferred": deferred}
         x = None if thin_in else inp[..., :self.cin]
         for i, conv in enumerate(self.layers):
             oh, ow = conv.out_size(*ws["s"][-1])
@@ -560,8 +574,19 @@ class DiscriminatorRuntime(_NetRuntimeBase):
                 y = conv.forward(x, oh, ow, bn_acc=sc["acc"] if fuse else None)
                 a = torch.empty_like(y)
                 ws["y"][i], ws["a"][i], ws["bn"][i] = y, a, sc
-                bn.forward(y, sc, training, a, ACT_LEAKY, stats_done=fuse)
+                bn.forward(y, sc, training, a, ACT_LEAKY, stats_done=fuse, deferred=deferred)
             x = a
+
+    def apply_deferred_running(self, ws):
+        """the running-statistics updates a forward(..., defer_running=True) left pending (must run before ws's backward,
+        which re-uses the statistic slots)"""
+        if ws.get("deferred") is None:
+            return
+        for bn, acc, count in ws["deferred"]:
+            bn.apply_running_update(acc, count)
+        if self.counters is not None:
+            self.counters.add_(1)
+        ws["deferred"] = None
 
     def backward(self, ws, dout, need_input_grad, param_grads=True):
         dt, dev = self.act_dtype, self.device()

@@ -163,6 +163,14 @@ def bn_finalize(acc, count, gamma, beta, rmean, rvar, momentum, eps, training, m
                                          mean_invstd.data_ptr(), scale_shift.data_ptr(), _stream()), "stcgan_bn_finalize")
 
 
+def bn_running_update(acc, count, rmean, rvar, momentum):
+    """the momentum update of the running statistics from the fp64 statistic slots `acc` (see stcgan_bn_running_update)."""
+    c = rmean.numel()
+    assert acc.dtype == torch.float64 and acc.is_contiguous() and acc.numel() == _lib.BN_SLOTS * 2 * c
+    check(_lib.load().stcgan_bn_running_update(acc.data_ptr(), int(count), c, rmean.data_ptr(), rvar.data_ptr(), float(momentum),
+                                               _stream()), "stcgan_bn_running_update")
+
+
 def bn_act_apply(y, scale_shift, out1, act1, out2=None, act2=ACT_NONE):
     n, h, w, c, ldy = _nhwc(y)
     n1, hc, wc, c1, ld1 = _nhwc(out1)

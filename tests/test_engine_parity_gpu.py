@@ -370,3 +370,24 @@ def test_train_step_512_geometry(cuda, lib, states):
     for n in ("D1", "D2"):
         gb = torch.cat([g.reshape(-1) for g in _packed_grads(b, nets_b, n)]).cpu()
         assert rel_err(gb, ga[n]) < 2e-2, (n, rel_err(gb, ga[n]))
+
+
+def test_deferred_running_statistics_equal_inline_update(cuda, lib, states):
+    """DiscriminatorRuntime.forward(defer_running=True) + apply_deferred_running == the inline update of
+    stcgan_bn_fused_apply, bit for bit (running_mean / running_var / num_batches_tracked after real -> fake)."""
+    x, m, y = (t.to(cuda) for t in O.make_istd_batch(3, 256, 256, seed=17))
+    y2 = y.flip(0).contiguous()
+    a = _build("bf16", cuda, states, names=("D2",))["D2"]
+    b = _build("bf16", cuda, states, names=("D2",))["D2"]
+    ra, rb = a.runtime(), b.runtime()
+    ra.forward([x, m, y], True); oa, _ = ra.forward([x, m, y2], True)
+    rb.forward([x, m, y], True); ob, ws = rb.forward([x, m, y2], True, defer_running=True)
+    mid = {k: v.clone() for k, v in b.state_dict().items() if "running" in k or "num_batches" in k}
+    rb.apply_deferred_running(ws)
+    torch.cuda.synchronize()
+    assert torch.equal(oa, ob)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if "running" in k or "num_batches" in k:
+            assert torch.equal(sa[k], sb[k]), k
+            assert not torch.equal(mid[k], sb[k]), k          # the update really was pending
