@@ -108,6 +108,16 @@ int stcgan_tapconv(int geom, int dtype, int backend,
 int stcgan_tapconv_bnstats(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp,
                            void* y, int OH, int OW, int Nout, int ldy, void* workspace, int64_t workspace_bytes,
                            double* bn_acc, void* stream);
+/* Inference form of the tensor-core convolution (bf16): eval-mode BatchNorm folded into the epilogue and up to two
+ * activated outputs -- replaces nn.Conv2d / nn.ConvTranspose2d + nn.BatchNorm2d(eval) + nn.LeakyReLU / nn.ReLU
+ * (src/models/stcgan_g.py:85-90,107-111 as executed by CGAN.infer, src/cgan.py:422-438) without materialising the
+ * pre-activation tensor:  v = acc * scale[c] + shift[c]  (scale NULL = 1, shift NULL = 0; for BatchNorm scale =
+ * gamma/sqrt(var+eps), shift = beta - mean*scale, i.e. stcgan_bn_finalize's scale_shift);  y = act(v);  y2 = act2(v) (y2 NULL
+ * = none).  Stores are cropped to [HC, WC] <= [OH, OW] (the odd-size crop of stcgan_g.py:131; y / y2 are [N, HC, WC, *]
+ * views with pitches ldy / ldy2).  act, act2 in {NONE, LEAKY, RELU}.  Workspace as stcgan_tapconv. */
+int stcgan_tapconv_ep(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp,
+                      const float* scale, const float* shift, int act, void* y, int ldy, int act2, void* y2, int ldy2,
+                      int OH, int OW, int HC, int WC, int Nout, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* weight gradient of the same convolutions:  G[t][d0][d1] += sum_p S[p, d0] * L[win_t(p), d1]
  * S : "small-grid" tensor [N, SH, SW, D0] pitch lds (Conv2d: dY; ConvTranspose2d: the layer input)
@@ -140,6 +150,12 @@ int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K,
  * t is zero-bordered [N, HP, WP, 8] bf16 (the border carries the conv padding), wthin [Nout][128] bf16 */
 int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
                     void* y, int OH, int OW, int Nout, int ldy, void* stream);
+/* the same convolution with TWO activated outputs of the one accumulator: y = act(v), y2 = act2(v).  This is the U-Net's
+ * first layer: its raw output feeds LeakyReLU (next down conv) and, through the skip concatenation, ReLU (the decoder) --
+ * src/models/stcgan_g.py:87,89,125 -- and neither needs the pre-activation tensor (sign(leaky(v)) == sign(v) serves the
+ * backward pass), so it is never written. */
+int stcgan_thinconv2(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
+                     void* y, int ldy, int act2, void* y2, int ldy2, int OH, int OW, int Nout, void* stream);
 /* G += sum_q window(t, q)[(tap,c)] * f[q, d]; G index = [wtap][d][c] if fat_is_dim0 else [wtap][c][d] with
  * wtap = flip ? 15 - tap : tap; t zero-bordered [N, HP, WP, 8] with thin_c real channels, f [N, FH, FW, Dfat] pitch ldf */
 int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_c, const void* f, int FH, int FW, int Dfat,

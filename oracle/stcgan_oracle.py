@@ -315,7 +315,7 @@ def discriminator_forward(sd, x, training=True, n_layers=3, use_sigmoid=False, n
 def cal_loss(c, label, ls=False):
     """AdversarialLoss.cal_loss (src/loss.py:79-84) -- note the inverted flag:
     ls=False -> MSE, ls=True -> BCE-with-logits."""
-    t = torch.as_tensor(label, dtype=c.dtype).expand_as(c)
+    t = torch.as_tensor(label, dtype=c.dtype, device=c.device).expand_as(c)
     return F.mse_loss(c, t) if not ls else F.binary_cross_entropy_with_logits(c, t)
 
 

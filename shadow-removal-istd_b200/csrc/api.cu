@@ -19,9 +19,9 @@ int tapwgrad_ffma(int geom, int dtype, const void* S, int N, int SH, int SW, int
 // tapconv_tc.cu
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
                void* y, int Nout, int ldy, cudaStream_t st, int thin_n, float* y32, float* ws, long long ws_bytes,
-               double* bn_acc);
+               double* bn_acc, const EpilogueExtra* ex);
 int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
-                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st);
+                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st, const EpilogueExtra* ex);
 int thinwgrad_tc(const void* t, int N, int HP, int WP, int s, int thin_c, const void* f, int FH, int FW, int Dfat, int ldf,
                  int fat_is_dim0, int flip, float* G, cudaStream_t st);
 int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
@@ -105,7 +105,7 @@ int stcgan_tapconv(int geom, int dtype, int backend, const void* x, int N, int I
   if (backend == STCGAN_BACKEND_TC) {
     if (dtype != STCGAN_BF16 || out_nchw_f32) return STCGAN_EUNSUPPORTED;
     return tapconv_tc(geom, g, x, K, ldx, wp, bias, act, y, Nout, ldy, as_stream(stream), 0, nullptr,
-                      static_cast<float*>(workspace), (long long)workspace_bytes, nullptr);
+                      static_cast<float*>(workspace), (long long)workspace_bytes, nullptr, nullptr);
   }
   if (backend != STCGAN_BACKEND_FFMA) return STCGAN_EINVAL;
   return tapconv_ffma(g, dtype, x, K, ldx, wp, bias, act, y, Nout, ldy, out_nchw_f32, as_stream(stream));
@@ -120,7 +120,23 @@ int stcgan_tapconv_bnstats(int geom, const void* x, int N, int IH, int IW, int K
   if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
   if (N == 0) return 0;
   return tapconv_tc(geom, g, x, K, ldx, wp, nullptr, STCGAN_ACT_NONE, y, Nout, ldy, as_stream(stream), 0, nullptr,
-                    static_cast<float*>(workspace), (long long)workspace_bytes, bn_acc);
+                    static_cast<float*>(workspace), (long long)workspace_bytes, bn_acc, nullptr);
+}
+
+int stcgan_tapconv_ep(int geom, const void* x, int N, int IH, int IW, int K, int ldx, const void* wp,
+                      const float* scale, const float* shift, int act, void* y, int ldy, int act2, void* y2, int ldy2,
+                      int OH, int OW, int HC, int WC, int Nout, void* workspace, int64_t workspace_bytes, void* stream) {
+  STCGAN_REQUIRE(x && wp && y);
+  STCGAN_REQUIRE(N >= 0 && IH > 0 && IW > 0 && OH > 0 && OW > 0 && K > 0 && Nout > 0 && ldx >= K && ldy >= Nout);
+  STCGAN_REQUIRE(HC > 0 && WC > 0 && HC <= OH && WC <= OW && (!y2 || ldy2 >= Nout));
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_RELU && act2 >= STCGAN_ACT_NONE && act2 <= STCGAN_ACT_RELU);
+  Geom g;
+  if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
+  if (N == 0) return 0;
+  EpilogueExtra ex;
+  ex.scale = scale; ex.y2 = y2; ex.ldy2 = ldy2; ex.act2 = act2; ex.HC = HC; ex.WC = WC;
+  return tapconv_tc(geom, g, x, K, ldx, wp, shift, act, y, Nout, ldy, as_stream(stream), 0, nullptr,
+                    static_cast<float*>(workspace), (long long)workspace_bytes, nullptr, &ex);
 }
 
 int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy,
@@ -219,14 +235,26 @@ int stcgan_tapconv_thin_n(int geom, const void* x, int N, int IH, int IW, int K,
   Geom g;
   if (!make_geom(geom, N, IH, IW, OH, OW, &g)) return STCGAN_EINVAL;
   if (N == 0) return 0;
-  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32, nullptr, 0, nullptr);
+  return tapconv_tc(geom, g, x, K, ldx, wp16, bias, act, y_nhwc8, Nout, ldy, as_stream(stream), 1, y_nchw_f32, nullptr, 0, nullptr,
+                    nullptr);
 }
 
 int stcgan_thinconv(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
                     void* y, int OH, int OW, int Nout, int ldy, void* stream) {
   STCGAN_REQUIRE(t && wthin && y && N >= 0 && HP >= 4 && WP >= 4 && (stride == 1 || stride == 2) && OH > 0 && OW > 0 && ldy >= Nout);
   if (N == 0) return 0;
-  return thinconv_tc(t, N, HP, WP, stride, wthin, bias, act, y, OH, OW, Nout, ldy, as_stream(stream));
+  return thinconv_tc(t, N, HP, WP, stride, wthin, bias, act, y, OH, OW, Nout, ldy, as_stream(stream), nullptr);
+}
+
+int stcgan_thinconv2(const void* t, int N, int HP, int WP, int stride, const void* wthin, const float* bias, int act,
+                     void* y, int ldy, int act2, void* y2, int ldy2, int OH, int OW, int Nout, void* stream) {
+  STCGAN_REQUIRE(t && wthin && y && y2 && N >= 0 && HP > 0 && WP > 0 && (stride == 1 || stride == 2));
+  STCGAN_REQUIRE(OH > 0 && OW > 0 && Nout > 0 && ldy >= Nout && ldy2 >= Nout);
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_RELU && act2 >= STCGAN_ACT_NONE && act2 <= STCGAN_ACT_RELU);
+  if (N == 0) return 0;
+  EpilogueExtra ex;
+  ex.y2 = y2; ex.ldy2 = ldy2; ex.act2 = act2;
+  return thinconv_tc(t, N, HP, WP, stride, wthin, bias, act, y, OH, OW, Nout, ldy, as_stream(stream), &ex);
 }
 
 int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_c, const void* f, int FH, int FW, int Dfat,

@@ -156,6 +156,14 @@ inline bool make_geom(int kind, int N, int IH, int IW, int OH, int OW, Geom* g) 
   }
 }
 
+// optional extras of a forward convolution's epilogue (tensor-core path):
+//   v = acc * scale[c] + bias[c]  ->  y = act(v),  y2 = act2(v);  stores cropped to [HC, WC] (0 = the layer's output size)
+struct EpilogueExtra {
+  const float* scale = nullptr;      // per output channel (nullptr = 1); the per-channel shift travels as `bias`
+  void* y2 = nullptr; int ldy2 = 0; int act2 = 0;
+  int HC = 0, WC = 0;
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace stcgan

@@ -57,7 +57,14 @@ struct alignas(64) TapGemmParams {
   int dbg_mode;            // timing experiments only (STCGAN_TC_DBGMODE): bit 0 = skip the MMAs, bit 1 = skip the TMA loads,
                            // bit 2 = fetch the weight tile as ONE contiguous bulk copy (wrong data: timing of a tile-major layout)
   const void* wp_raw;
+  // extended epilogue (inference: eval-mode BatchNorm folded into the convolution; dual activation of the U-Net skip):
+  //   v = acc * ep_scale[c] + bias[c]   (ep_scale == nullptr: 1)   ->  y = act(v),  y2 = act2(v)  (y2 == nullptr: none)
+  // OH / OW above are the STORE extent (a cropped destination has OH, OW smaller than the layer's true output size)
+  const float* ep_scale;
+  __nv_bfloat16* y2;
+  int ldy2, act2;
 };
+
 
 __device__ __forceinline__ long long gtime() {
   long long t;
@@ -254,19 +261,27 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         }
       }
     } else if (P.part_out == nullptr) {
-      // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced
+      // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced.  With a second
+      // output (P.y2) the accumulators are read from TMEM a second time and go through the same staging rows.
       constexpr int PITCH = BN * 2 + 16;
-      const float slope = act_slope(P.act);
       const float* bias = P.bias;
+      const float* scale = P.ep_scale;
+      const int npass = P.y2 ? 2 : 1;
+#pragma unroll 1
+      for (int op = 0; op < npass; ++op) {
+      const float slope = act_slope(op == 0 ? P.act : P.act2);
+      __nv_bfloat16* const ybase = op == 0 ? P.y : P.y2;
+      const int ldo = op == 0 ? P.ldy : P.ldy2;
+      if (op) __syncwarp();                     // this warp's row stores of the first pass have read the staging rows
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        if (mt > 0) {                           // rows 128.. of the tile live in the second accumulator
+        {                                       // rows mt*128.. of the tile live in accumulator mt
           row = mt * TC_BM + q * 32 + lane;
           wl = row % P.wt; hl = (row / P.wt) % P.ht; nl = row / (P.wt * P.ht);
           a = a0 + hl; b = b0 + wl; n = n0 + nl;
           oy = a * P.ostride + P.oy0[cls]; ox = b * P.ostride + P.ox0[cls];
           valid = n < P.N && oy < P.OH && ox < P.OW;
-          out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
+          out = ybase + ((long long)(n * P.OH + oy) * P.OW + ox) * ldo + n_col0;
         }
         const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
 #pragma unroll 1
@@ -285,6 +300,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+              if (scale) { f0 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e); f1 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e + 1); }
               if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
               f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
               const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
@@ -308,6 +324,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
             *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
           }
         }
+      }
       }
       if (P.bn_acc) {
         // BatchNorm statistics of this tile from the staged bf16 values: thread (rg, cg) sums 8 channels over its row
@@ -504,6 +521,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
     const int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
     const float slope = act_slope(P.act);
     const float* bias = P.bias;
+    const float* scale = P.ep_scale;
     const uint32_t stg = smem_u32(smem + SM::STAGING_OFFSET) + (uint32_t)row * SM::PITCH;
     const uint32_t wbase = smem_u32(smem + SM::STAGING_OFFSET) + (uint32_t)(q * 32) * SM::PITCH;
     constexpr int LPR = BN * 2 / 16;
@@ -519,37 +537,48 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
       const uint32_t buf = li & 1u;
       mbar_wait_warp(&tmem_full[buf], (li >> 1) & 1u, lane);
       tc_fence_after();
-      __syncwarp();                                   // previous tile's row stores of this warp have read the staging rows
+      const int npass = P.y2 ? 2 : 1;                 // second output: the accumulators are read twice (see TapGemmParams)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, r);
+      for (int op = 0; op < npass; ++op) {
+        const float slope_o = op == 0 ? slope : act_slope(P.act2);
+        __nv_bfloat16* const out_o = op == 0 ? out : P.y2 + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy2 + n_col0;
+        __syncwarp();                                 // previous row stores of this warp have read the staging rows
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, r);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t w[4];
+          for (int v = 0; v < 4; ++v) {
+            uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-            if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
-            f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+              if (scale) { f0 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e); f1 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e + 1); }
+              if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+              f0 = act_piecewise(f0, slope_o); f1 = act_piecewise(f1, slope_o);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              w[e] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
           }
-          st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
         }
-      }
-      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+        if (op == npass - 1) {
+          // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld): hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        } else {
+          __syncwarp();
+        }
+        const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out_o) : 0ull;
 #pragma unroll 4
-      for (int i = 0; i < 32; i += RPI) {
-        const int rr = i + lane / LPR;
-        const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
-        if (pr) {
-          const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * SM::PITCH + (lane % LPR) * 16);
-          *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+        for (int i = 0; i < 32; i += RPI) {
+          const int rr = i + lane / LPR;
+          const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+          if (pr) {
+            const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * SM::PITCH + (lane % LPR) * 16);
+            *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+          }
         }
       }
     }
@@ -1104,53 +1133,98 @@ static int persistent_mode() {
 // thin_n != 0: Nout <= 16 real output channels, wp packed with 16 (zero-padded) rows per tap; output goes to y32
 // (NCHW fp32, bias + any activation) or, if y32 == NULL, to the first 8 channels of an NHWC bf16 tensor.
 // fp32 split-K partial sums [P][Nout] -> bf16 y (pitch ldy) with bias + activation
+struct FinishExtra {          // see EpilogueExtra; OW/OH = true output extent of the partial sums, HC/WC = store crop
+  const float* scale; __nv_bfloat16* y2; int ldy2, act2; int OH, OW, HC, WC;
+};
+
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(float* __restrict__ part, long long P, int Nout, const float* __restrict__ bias, int act,
-                     __nv_bfloat16* __restrict__ y, int ldy, double* __restrict__ bn_acc, int clear) {
+                     __nv_bfloat16* __restrict__ y, int ldy, double* __restrict__ bn_acc, int clear, const FinishExtra ex) {
   pdl_prologue();
   const int quads = Nout / 4;
   const float slope = act_slope(act);
   if (bn_acc == nullptr) {
+    const float slope2 = act_slope(ex.act2);
+    const bool crop = ex.HC != ex.OH || ex.WC != ex.OW;
     const long long total = P * quads;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
       const long long p = i / quads; const int c = (int)(i % quads) * 4;
       const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
       if (clear) *reinterpret_cast<float4*>(part + p * Nout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      float f[4] = {v.x, v.y, v.z, v.w};
+      long long pd = p;
+      if (crop) {                                   // destination pixel inside the cropped extent (or skipped)
+        const int ox = (int)(p % ex.OW); const long long t = p / ex.OW;
+        const int oy = (int)(t % ex.OH); const long long n = t / ex.OH;
+        if (oy >= ex.HC || ox >= ex.WC) continue;
+        pd = (n * ex.HC + oy) * ex.WC + ox;
+      }
+      float f[4] = {v.x, v.y, v.z, v.w}, g[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float z = f[e] * (ex.scale ? ex.scale[c + e] : 1.f) + (bias ? bias[c + e] : 0.f);
+        f[e] = act_piecewise(z, slope); g[e] = act_piecewise(z, slope2);
+      }
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+      uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(y + pd * ldy + c) = o;
+      if (ex.y2) {
+        const __nv_bfloat162 k0 = __floats2bfloat162_rn(g[0], g[1]), k1 = __floats2bfloat162_rn(g[2], g[3]);
+        uint2 o2; o2.x = *reinterpret_cast<const uint32_t*>(&k0); o2.y = *reinterpret_cast<const uint32_t*>(&k1);
+        *reinterpret_cast<uint2*>(ex.y2 + pd * ex.ldy2 + c) = o2;
+      }
+    }
+    return;
+  }
+  // with BatchNorm statistics (host guarantees quads <= 256 and 256 % quads == 0): a thread keeps one channel quad and
+  // walks down the rows (four independent row loads in flight); per-thread fp32 sums of the bf16-rounded outputs are combined
+  // across the block's row groups in shared memory, then ONE fp64 atomic pair per channel and block goes into slot
+  // blockIdx.x % SLOTS (round 1 issued them per thread: 262 k contended fp64 atomics made this kernel slower than the GEMM)
+  __shared__ float red[2 * 256 * 4];
+  const int qd = threadIdx.x % quads, rr = threadIdx.x / quads, rpb = 256 / quads, c = qd * 4;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long p0 = (long long)blockIdx.x * rpb + rr; p0 < P; p0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * stride;
+      v[u] = p < P ? *reinterpret_cast<const float4*>(part + p * Nout + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * stride;
+      if (p >= P) continue;
+      if (clear) *reinterpret_cast<float4*>(part + p * Nout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
       const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
       uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
+      const float r[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s4[e] += r[e]; q4[e] = fmaf(r[e], r[e], q4[e]); }
     }
-    return;
   }
-  // with BatchNorm statistics (host guarantees quads <= 256 and 256 % quads == 0): a thread keeps one channel quad and
-  // walks down the rows; per-thread fp32 sums of the bf16-rounded outputs, then fp64 atomics into slot blockIdx.x % SLOTS
-  const int qd = threadIdx.x % quads, rr = threadIdx.x / quads, rpb = 256 / quads, c = qd * 4;
-  float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long p = (long long)blockIdx.x * rpb + rr; p < P; p += (long long)gridDim.x * rpb) {
-    const float4 v = *reinterpret_cast<const float4*>(part + p * Nout + c);
-    if (clear) *reinterpret_cast<float4*>(part + p * Nout + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) f[e] = act_piecewise(f[e] + (bias ? bias[c + e] : 0.f), slope);
-    const __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-    uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(y + p * ldy + c) = o;
-    const float r[4] = {__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1)};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { s4[e] += r[e]; q4[e] = fmaf(r[e], r[e], q4[e]); }
-  }
+  for (int e = 0; e < 4; ++e) { red[rr * Nout + c + e] = s4[e]; red[1024 + rr * Nout + c + e] = q4[e]; }
+  __syncthreads();
   double* acc = bn_acc + (long long)(blockIdx.x % STCGAN_BN_SLOTS) * 2 * Nout;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { atomicAdd(acc + c + e, (double)s4[e]); atomicAdd(acc + Nout + c + e, (double)q4[e]); }
+  for (int j = threadIdx.x; j < Nout; j += 256) {
+    float ts = 0.f, tq = 0.f;
+    for (int g2 = 0; g2 < rpb; ++g2) { ts += red[g2 * Nout + j]; tq += red[1024 + g2 * Nout + j]; }
+    atomicAdd(acc + j, (double)ts);
+    atomicAdd(acc + Nout + j, (double)tq);
+  }
 }
 
 int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, const void* wp, const float* bias, int act,
                void* y, int Nout, int ldy, cudaStream_t st, int thin_n = 0, float* y32 = nullptr,
-               float* ws = nullptr, long long ws_bytes = 0, double* bn_acc = nullptr) {
+               float* ws = nullptr, long long ws_bytes = 0, double* bn_acc = nullptr, const EpilogueExtra* ex = nullptr) {
   if (bn_acc && (thin_n || act != STCGAN_ACT_NONE || Nout % 64 != 0)) return STCGAN_EUNSUPPORTED;
+  if (ex && (bn_acc || thin_n)) return STCGAN_EUNSUPPORTED;
+  if (ex && ex->y2 && (ex->ldy2 % 8 != 0 || !al16(ex->y2) || ex->act2 == STCGAN_ACT_TANH || ex->act2 == STCGAN_ACT_SIGMOID))
+    return STCGAN_EUNSUPPORTED;
   // ws_bytes < 0: the workspace (|ws_bytes| bytes) is all zeros on entry and is left all zeros on exit (the finisher clears
   // what it reads): a persistent workspace saves the memset launch in front of every split-K convolution
   const bool ws_clean = ws_bytes < 0;
@@ -1201,6 +1275,17 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
   P.GH = GH; P.GW = GW; P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.ostride = g.ostride;
   P.ntaps = g.ntaps; P.kchunks = K / 64;
   P.Nout = Nout; P.ldy = ldy; P.act = act; P.bias = bias; P.y = static_cast<__nv_bfloat16*>(y);
+  FinishExtra fx;
+  fx.scale = nullptr; fx.y2 = nullptr; fx.ldy2 = 0; fx.act2 = 0; fx.OH = g.OH; fx.OW = g.OW; fx.HC = g.OH; fx.WC = g.OW;
+  if (ex) {
+    P.ep_scale = ex->scale; P.y2 = static_cast<__nv_bfloat16*>(ex->y2); P.ldy2 = ex->ldy2; P.act2 = ex->act2;
+    fx.scale = ex->scale; fx.y2 = P.y2; fx.ldy2 = ex->ldy2; fx.act2 = ex->act2;
+    if (ex->HC > 0 && ex->WC > 0) {
+      if (ex->HC > g.OH || ex->WC > g.OW) return STCGAN_EINVAL;
+      P.OH = ex->HC; P.OW = ex->WC;           // store extent (the tile grid below still covers the layer's true output)
+      fx.HC = ex->HC; fx.WC = ex->WC;
+    }
+  }
 
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   const long long sn = (long long)g.IH * g.IW * ldx;
@@ -1240,12 +1325,13 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
     const int bn_s = Nout % 128 == 0 ? 128 : 64;
     const long long ctas_s = (long long)P.tiles_w * P.tiles_h * tiles_n * (Nout / bn_s) * g.nclass;
     const long long need_s = (long long)g.N * g.OH * g.OW * Nout * 4;
+    P.OH = g.OH; P.OW = g.OW;                 // (partial sums always cover the true output; the finisher crops)
     if (ws && ws_bytes >= need_s && ctas_s <= 74 && g.ntaps * P.kchunks >= 32 && MTsel == 1) {
       while (ksplit * 2 <= g.ntaps && ctas_s * ksplit * 2 <= 296) ksplit *= 2;
       if (ksplit > 1) BNsel = bn_s;
     }
   }
-  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc ? 128 : BNsel));
+  rc = encode_2d(&P.bmap, wp, K, 16LL * n_rows, thin_n ? 16 : (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc && !ex ? 128 : BNsel));
   if (rc) return rc;
 
   for (int c = 0; c < g.nclass; ++c)
@@ -1287,23 +1373,24 @@ int tapconv_tc(int geom_kind, const Geom& g, const void* x, int K, int ldx, cons
       const int quads = Nout / 4;
       if (quads > 256 || 256 % quads != 0) return STCGAN_EUNSUPPORTED;
       const int rpb = 256 / quads;
-      blocks = (Ppix + rpb * 4 - 1) / (rpb * 4); if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
+      blocks = (Ppix + rpb * 8 - 1) / (rpb * 8); if (blocks > 148) blocks = 148; if (blocks < 1) blocks = 1;
     }
     P.bn_acc = nullptr;     // (the GEMM launch above already ran; statistics come from the finished sums)
     launch_k(splitk_finish_kernel, (unsigned)blocks, 256, 0, st, ws, Ppix, Nout, bias, act, static_cast<__nv_bfloat16*>(y), ldy, bn_acc,
-             ws_clean ? 1 : 0);
+             ws_clean ? 1 : 0, fx);
     return finish_launch();
   }
+  if (ex && ex->HC > 0 && ex->WC > 0) { P.OH = ex->HC; P.OW = ex->WC; }
   if (MTsel == 2) {
     if (BNsel == 256) BNsel = 128;
     dim3 grid2((unsigned)(P.tiles_w * P.tiles_h * tiles_n), (unsigned)(Nout / BNsel), (unsigned)g.nclass);
     return BNsel == 128 ? launch_tapgemm<128, 2, 2>(P, grid2, st) : launch_tapgemm<64, 2, 2>(P, grid2, st);
   }
-  if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
+  if (pair_mode() == 1 && Nout % 256 == 0 && ksplit == 1 && !bn_acc && !ex) {   // each CTA stages 128 of the 256 weight rows (TMA box of 128)
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     return launch_tapgemm_pair<256, 3>(P, m_tiles, Nout / 256, g.nclass, st);
   }
-  if (persistent_mode() == 1 && BN != 256 && !bn_acc) {
+  if (persistent_mode() == 1 && BN != 256 && !bn_acc && !ex) {
     const int m_tiles = P.tiles_w * P.tiles_h * tiles_n;
     if (BN == 128) return launch_tapgemm_persistent<128, 5>(P, m_tiles, Nout / BN, g.nclass, st);
     return launch_tapgemm_persistent<64, 6>(P, m_tiles, Nout / BN, g.nclass, st);
@@ -1380,9 +1467,11 @@ static int encode_nhwc_blk(CUtensorMap* m, const void* base, long long C, long l
 // thin-K convolution: out[p, n] = sum_{kh,kw,c} T[window(p)][kh][kw][c] * Wt[n][(kh*4+kw)*8 + c]
 //   T: zero-bordered [N, HP, WP, 8] bf16; output grid OH x OW with window anchor (s*oy, s*ox) in padded coordinates
 int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, const float* bias, int act,
-                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st) {
+                void* y, int OH, int OW, int Nout, int ldy, cudaStream_t st, const EpilogueExtra* ex = nullptr) {
   if (Nout % 64 != 0 || ldy % 8 != 0 || !al16(t) || !al16(y) || !al16(wthin)) return STCGAN_EUNSUPPORTED;
   if (act == STCGAN_ACT_TANH || act == STCGAN_ACT_SIGMOID) return STCGAN_EUNSUPPORTED;
+  if (ex && ex->y2 && (ex->ldy2 % 8 != 0 || !al16(ex->y2) || ex->act2 == STCGAN_ACT_TANH || ex->act2 == STCGAN_ACT_SIGMOID))
+    return STCGAN_EUNSUPPORTED;
   if (s * (OH - 1) + 4 > HP || s * (OW - 1) + 4 > WP) return STCGAN_EINVAL;     // windows must stay inside the border
   TapGemmParams P;
   memset(&P, 0, sizeof(P));
@@ -1392,6 +1481,7 @@ int thinconv_tc(const void* t, int N, int HP, int WP, int s, const void* wthin, 
   P.GH = OH; P.GW = OW; P.N = N; P.OH = OH; P.OW = OW; P.ostride = 1;
   P.ntaps = 1; P.kchunks = 2; P.thin_k = 1;
   P.Nout = Nout; P.nout_real = Nout; P.ldy = ldy; P.act = act; P.bias = bias; P.y = static_cast<__nv_bfloat16*>(y);
+  if (ex) { P.ep_scale = ex->scale; P.y2 = static_cast<__nv_bfloat16*>(ex->y2); P.ldy2 = ex->ldy2; P.act2 = ex->act2; }
   int rc = encode_thin5d(&P.amap[0], t, HP, WP, N, s, OW, OH, P.wt, P.ht, P.nt, 2);
   if (rc) return rc;
   for (int v = 1; v < 4; ++v) P.amap[v] = P.amap[0];

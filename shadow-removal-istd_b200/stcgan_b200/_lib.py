@@ -48,6 +48,8 @@ SIGNATURES = {
     "stcgan_launch_count_reset": (None, []),
     "stcgan_tapconv": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _i64, _p]),
     "stcgan_tapconv_bnstats": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i64, _p, _p]),
+    "stcgan_tapconv_ep": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i64, _p]),
+    "stcgan_thinconv2": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p]),
     "stcgan_bn_fused_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _f, _f, _i, _p, _p, _i, _i,
                                    _p, _i, _i, _p, _i, _i, _p]),
     "stcgan_tapwgrad": (_i, [_i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),

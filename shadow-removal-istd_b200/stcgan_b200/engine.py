@@ -635,8 +635,12 @@ def infer(G1, G2, x, quantize=True):
         raise RuntimeError("infer() expects G1.eval(); G2.eval() like the reference (cgan.py:422-423)")
     rt1, rt2 = G1.runtime(), G2.runtime()
     x = x.contiguous()
-    mp, _ = rt1.forward([x], False)
-    yp, _ = rt2.forward([x, mp], False)
+    if os.environ.get("STCGAN_INFER_FOLD", "1") != "0":
+        mp = rt1.forward_inference([x])             # BatchNorm(eval) + activations folded into the conv epilogues
+        yp = rt2.forward_inference([x, mp])
+    else:
+        mp, _ = rt1.forward([x], False)
+        yp, _ = rt2.forward([x, mp], False)
     if not quantize:
         return mp, yp, None, None
     return mp, yp, ops.float2uint_hwc(mp), ops.float2uint_hwc(yp)

@@ -441,6 +441,64 @@ class GeneratorRuntime(_NetRuntimeBase):
         ws["out"] = out
         return out, ws
 
+    def forward_inference(self, sources, packed=None):
+        """Eval-mode forward that keeps nothing for a backward pass (CGAN.infer, src/cgan.py:422-438).  On the bf16 tensor-core
+        path every BatchNorm(eval) + LeakyReLU / ReLU is folded into the producing convolution's epilogue (per-channel scale /
+        shift from the running statistics, stcgan_tapconv_ep), the encoder writes both activations of a level -- LeakyReLU for
+        the next down conv, ReLU into the left half of the decoder's concat buffer -- from one accumulator, and the decoder's
+        odd-size crop (stcgan_g.py:131) is a store bound: no pre-activation tensor is written or re-read, no BatchNorm pass
+        runs.  Falls back to forward(training=False) where a layer is not eligible (fp32 mode, narrow networks)."""
+        self.ensure_packed()
+        L = self.L
+        fold_ok = (self.act_dtype == torch.bfloat16 and self.downs[0].thin == "cin" and self.ups[0].thin == "coutT"
+                   and all(c.use_tc and c.thin is None and ops.tc_eligible_conv(c.cin, c.cout)
+                           for c in list(self.downs[1:]) + list(self.ups[1:])))
+        inp, inp_b = self._packed_input(sources, packed)
+        if not fold_ok or inp_b is None:
+            return self.forward(sources, False, packed=packed)[0]
+        dt, dev = self.act_dtype, self.device()
+        n, _, h, w = sources[0].shape
+        s = self.sizes(h, w)
+        C = [None] + [d.cout for d in self.downs]
+        new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
+
+        def folded(bn):             # eval-mode BatchNorm as per-channel (scale, shift): fp32 [2, C]
+            m = bn.m
+            ss = torch.empty((2, bn.c), dtype=torch.float32, device=dev)
+            mi = torch.empty((2, bn.c), dtype=torch.float32, device=dev)
+            ops.bn_finalize(None, 0, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_var, 0.0, m.eps, False, mi, ss)
+            return ss
+
+        cats = [None] * (L + 1)
+        # ---- encoder
+        x = None
+        for k in range(1, L + 1):
+            hk, wk = s[k]
+            down = self.downs[k - 1]
+            if k == L:              # innermost: no BatchNorm, ReLU feeds the up conv
+                x = ops.tapconv_ep(GEOM_WIN_S2, x, down.p1, C[k], hk, wk, act=ACT_RELU)
+                break
+            a, cat = new(hk, wk, C[k]), new(hk, wk, 2 * C[k])
+            cats[k] = cat
+            if k == 1:              # outermost: no BatchNorm; thin-K first layer, two activations of one accumulator
+                ops.thinconv2(inp_b, 2, down.wthin, C[k], hk, wk, act=ACT_LEAKY, out=a, act2=ACT_RELU, out2=cat[..., :C[k]])
+            else:
+                ops.tapconv_ep(GEOM_WIN_S2, x, down.p1, C[k], hk, wk, scale_shift=folded(self.down_bns[k - 1]), act=ACT_LEAKY,
+                               out=a, act2=ACT_RELU, out2=cat[..., :C[k]])
+            x = a
+        # ---- decoder
+        for k in range(L, 1, -1):
+            hk, wk = s[k]
+            up = self.ups[k - 1]
+            dst = cats[k - 1]
+            ops.tapconv_ep(GEOM_PARITY, x, up.p2, up.cout, 2 * hk, 2 * wk, scale_shift=folded(self.up_bns[k - 1]), act=ACT_RELU,
+                           out=dst[..., C[k - 1]:], crop=(dst.shape[1], dst.shape[2]))
+            x = dst
+        h1, w1 = s[1]
+        out = torch.empty((n, self.cout, 2 * h1, 2 * w1), dtype=torch.float32, device=dev)
+        self.ups[0].forward(x, 2 * h1, 2 * w1, out_nchw=out, act=ACT_TANH)
+        return out
+
     def backward(self, ws, dout, need_input_grad, param_grads=True, part=None):
         """dout: NCHW fp32 gradient of the output.  Accumulates parameter gradients into the flat buffer;
         returns the NHWC gradient of the packed input (or None).

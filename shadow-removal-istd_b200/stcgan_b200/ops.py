@@ -120,6 +120,59 @@ def tapconv(geom, x, wp, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, out
     return y
 
 
+def _splitk_ws(n_elems, device):
+    """persistent, self-cleaning split-K workspace of this size for the current stream (see _SPLITK_WS)"""
+    key = (n_elems, device.index, torch.cuda.current_stream().cuda_stream)
+    wst = _SPLITK_WS.get(key)
+    if wst is None:
+        wst = _SPLITK_WS[key] = torch.zeros(n_elems, dtype=torch.float32, device=device)
+    return wst
+
+
+def tapconv_ep(geom, x, wp, nout, oh, ow, *, scale_shift=None, shift=None, act=ACT_NONE, out=None, act2=ACT_NONE, out2=None,
+               crop=None):
+    """Inference convolution (bf16 tensor cores): v = acc * scale + shift, out = act(v) [, out2 = act2(v)], stores cropped
+    to `crop` = (HC, WC).  `scale_shift`: fp32 [2, nout] as written by bn_finalize (eval-mode BatchNorm folded into the
+    epilogue); `shift` alone = a conv bias.  `out` / `out2` may be channel-slice views of [N, HC, WC, *] buffers."""
+    _need_cuda(x, wp)
+    n, ih, iw, k, ldx = _nhwc(x)
+    hc, wc = crop if crop is not None else (oh, ow)
+    if out is None:
+        out = torch.empty((n, hc, wc, nout), dtype=x.dtype, device=x.device)
+    assert tuple(out.shape) == (n, hc, wc, nout) and x.dtype == torch.bfloat16
+    _, _, _, _, ldy = _nhwc(out)
+    ld2 = 0
+    if out2 is not None:
+        assert tuple(out2.shape) == (n, hc, wc, nout)
+        _, _, _, _, ld2 = _nhwc(out2)
+    sc = sh = None
+    if scale_shift is not None:
+        assert scale_shift.dtype == torch.float32 and scale_shift.is_contiguous() and scale_shift.numel() == 2 * nout
+        sc, sh = scale_shift.data_ptr(), scale_shift.data_ptr() + 4 * nout
+    elif shift is not None:
+        sh = shift.data_ptr()
+    ws, ws_bytes = None, 0
+    if n * oh * ow * nout <= SPLITK_MAX_ELEMS and k >= 256:
+        wst = _splitk_ws(n * oh * ow * nout, x.device)
+        ws, ws_bytes = wst.data_ptr(), -wst.numel() * 4
+    check(_lib.load().stcgan_tapconv_ep(geom, x.data_ptr(), n, ih, iw, k, ldx, wp.data_ptr(), sc, sh, act, out.data_ptr(), ldy,
+                                        act2, None if out2 is None else out2.data_ptr(), ld2, oh, ow, hc, wc, nout, ws, ws_bytes,
+                                        _stream()), "stcgan_tapconv_ep")
+    return out
+
+
+def thinconv2(t, stride, wthin, nout, oh, ow, *, bias=None, act=ACT_NONE, out=None, act2=ACT_NONE, out2=None):
+    """thin-K convolution with two activated outputs (see stcgan_thinconv2)."""
+    n, hp, wp_, c, _ = _nhwc(t)
+    assert c == 8 and t.is_contiguous() and t.dtype == torch.bfloat16 and out is not None and out2 is not None
+    _, _, _, _, ldy = _nhwc(out)
+    _, _, _, _, ld2 = _nhwc(out2)
+    check(_lib.load().stcgan_thinconv2(t.data_ptr(), n, hp, wp_, stride, wthin.data_ptr(),
+                                       None if bias is None else bias.data_ptr(), act, out.data_ptr(), ldy, act2,
+                                       out2.data_ptr(), ld2, oh, ow, nout, _stream()), "stcgan_thinconv2")
+    return out
+
+
 def tapwgrad(geom, s, l, g, *, backend=BACKEND_FFMA):
     """g[16, D0, D1] (fp32) += wgrad(S small-grid tensor, L large-grid tensor)."""
     _need_cuda(s, l, g)

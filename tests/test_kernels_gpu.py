@@ -461,3 +461,80 @@ def test_optional_tensor_core_kernels_stay_parity_green(cuda, lib, env):
     """)
     r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+EP_CASES = [
+    # kind, cin, cout, n, h, w, crop (rows / columns dropped from the output extent)
+    ("conv2", 64, 128, 4, 32, 32, (0, 0)),      # encoder level: BN + LeakyReLU / ReLU, two outputs
+    ("conv2", 128, 64, 3, 15, 21, (0, 0)),      # odd input (TMA zero fill), BN = 64 tiles
+    ("conv2", 64, 128, 6, 128, 128, (0, 0)),    # two-accumulator tiles (MT = 2)
+    ("conv2", 512, 512, 4, 4, 6, (0, 0)),       # split-K path: the finisher applies scale / shift / both activations
+    ("convT", 128, 64, 2, 16, 16, (0, 0)),      # decoder level
+    ("convT", 1024, 512, 2, 8, 10, (1, 0)),     # decoder level with the odd-size crop (16x20 -> 15x20), 128x256-tile candidate
+    ("convT", 1024, 512, 2, 2, 3, (0, 1)),      # split-K + crop (4x6 -> 4x5)
+    ("convT", 512, 256, 64, 15, 20, (0, 0)),    # inference-sized launch (multi-wave)
+]
+
+
+@pytest.mark.parametrize("case", EP_CASES, ids=lambda c: "-".join(map(str, c)))
+def test_conv_inference_epilogue_folds_eval_batchnorm(cuda, lib, case):
+    """stcgan_tapconv_ep: eval-mode BatchNorm (per-channel scale / shift from the running statistics) + two activations + the
+    odd-size crop folded into the convolution's epilogue == nn.Conv2d / nn.ConvTranspose2d -> nn.BatchNorm2d.eval() ->
+    LeakyReLU / ReLU -> [:, :, :H, :W] of the reference (src/models/stcgan_g.py:85-90, 107-111, 131)."""
+    from stcgan_b200 import ops
+    from stcgan_b200._lib import ACT_LEAKY, ACT_RELU, GEOM_PARITY, GEOM_WIN_S2
+    kind, cin, cout, n, h, w_, (dh, dw) = case
+    op, w, _ = _convop(kind, cin, cout, "bf16", cuda)
+    g = torch.Generator().manual_seed(7)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), "bf16")
+    ph, pw = (h + h % 2, w_ + w_ % 2) if kind == "conv2" else (h, w_)
+    oh, ow = op.out_size(ph, pw)
+    hc, wc = oh - dh, ow - dw
+    bn = torch.nn.BatchNorm2d(cout).double().eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(cout, generator=g) + 0.5); bn.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(cout, generator=g) * 0.2); bn.running_var.copy_(torch.rand(cout, generator=g) + 0.5)
+    f32 = lambda t: t.detach().float().to(cuda)
+    ss = torch.empty((2, cout), device=cuda); mi = torch.empty((2, cout), device=cuda)
+    ops.bn_finalize(None, 0, f32(bn.weight), f32(bn.bias), f32(bn.running_mean), f32(bn.running_var), 0.0, 1e-5, False, mi, ss)
+    wide = torch.zeros((n, hc, wc, 2 * cout), dtype=torch.bfloat16, device=cuda)      # out2 = a channel-slice view
+    geom = GEOM_PARITY if kind == "convT" else GEOM_WIN_S2
+    wp = op.p2 if kind == "convT" else op.p1
+    a = ops.tapconv_ep(geom, _nhwc(x, torch.bfloat16, cuda), wp, cout, oh, ow, scale_shift=ss, act=ACT_LEAKY,
+                       act2=ACT_RELU, out2=wide[..., cout:], crop=(hc, wc))
+    torch.cuda.synchronize()
+    xp = F.pad(x.double(), (0, pw - w_, 0, ph - h)) if kind == "conv2" else x.double()
+    z = bn(_ref_forward(kind, xp, _round(w, "bf16").double(), None))[:, :, :hc, :wc]
+    assert tuple(a.shape) == (n, hc, wc, cout)
+    assert rel_err(_nchw(a), F.leaky_relu(z, 0.2)) < 6e-3
+    assert rel_err(_nchw(wide[..., cout:]), F.relu(z)) < 6e-3
+    assert float(wide[..., :cout].abs().max()) == 0.0                                  # the other half of the buffer is untouched
+    # single output, plain shift (a bias) instead of BatchNorm
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    r = ops.tapconv_ep(geom, _nhwc(x, torch.bfloat16, cuda), wp, cout, oh, ow, shift=b, act=ACT_RELU, crop=(hc, wc))
+    torch.cuda.synchronize()
+    ref = F.relu(_ref_forward(kind, xp, _round(w, "bf16").double(), b.double().cpu()))[:, :, :hc, :wc]
+    assert rel_err(_nchw(r), ref) < 6e-3
+
+
+@pytest.mark.parametrize("cin,n,h,w_", [(3, 2, 64, 64), (4, 3, 30, 40)])
+def test_thin_first_layer_with_two_activations(cuda, lib, cin, n, h, w_):
+    """stcgan_thinconv2: the U-Net's first Conv2d with both consumers' activations (LeakyReLU for the next down conv, ReLU for
+    the skip concatenation, src/models/stcgan_g.py:87,89,125) from one accumulator == the two-pass form."""
+    from stcgan_b200 import ops
+    from stcgan_b200._lib import ACT_LEAKY, ACT_RELU
+    op, w, _ = _convop("conv2", cin, 64, "bf16", cuda)
+    assert op.thin == "cin"
+    g = torch.Generator().manual_seed(3)
+    x = _round(torch.randn(n, cin, h, w_, generator=g), "bf16")
+    xb = ops.pack_input([x.to(cuda).contiguous()], 8, torch.bfloat16, border=1)
+    oh, ow = op.out_size(h, w_)
+    a = torch.empty((n, oh, ow, 64), dtype=torch.bfloat16, device=cuda)
+    cat = torch.zeros((n, oh, ow, 128), dtype=torch.bfloat16, device=cuda)
+    ops.thinconv2(xb, 2, op.wthin, 64, oh, ow, act=ACT_LEAKY, out=a, act2=ACT_RELU, out2=cat[..., :64])
+    y = ops.thinconv(xb, 2, op.wthin, 64, oh, ow)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), _round(w, "bf16").double(), None, 2, 1)
+    assert rel_err(_nchw(a), F.leaky_relu(ref, 0.2)) < 6e-3 and rel_err(_nchw(cat[..., :64]), F.relu(ref)) < 6e-3
+    assert torch.equal(a, F.leaky_relu(y.float(), 0.2).to(torch.bfloat16)) and torch.equal(cat[..., :64], F.relu(y))
+    assert float(cat[..., 64:].abs().max()) == 0.0
