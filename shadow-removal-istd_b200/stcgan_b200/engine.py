@@ -215,6 +215,11 @@ class STCGANEngine:
         self.pg, self.world = process_group, self.sync.world
         self.optim_G.grad_scale = self.optim_D.grad_scale = 1.0 / self.world
         self.losses = torch.zeros(8, dtype=torch.float32, device=self.device)
+        # schedule switches (experiments / A-B measurements; the defaults are the measured-best combination)
+        flag = lambda name, default: os.environ.get(name, default) != "0"
+        self._early_d1 = conc and flag("STCGAN_EARLY_D1", "1")        # D1's exchange + Adam share + G-phase passes under G2's forward
+        self._adam_early = conc and flag("STCGAN_ADAM_EARLY", "1")    # G2's / G1.ups' Adam shares under the halves of G1's backward
+        self._overlap_real = conc and flag("STCGAN_OVERLAP_REAL", "1")  # D2's G-phase real pass next to its fake pass
         self._graph = None
         self._graphs = []
         self._static = None
@@ -335,15 +340,16 @@ class STCGANEngine:
                 # D1 is complete long before D2 (whose fake pass needs G2's forward): its gradient bucket goes on the wire
                 # now, its share of optim_D.step (cgan.py:305) and its two G-phase forward passes (cgan.py:321-322, with
                 # the UPDATED discriminator) follow on this lane, all underneath G2's forward and D2's fake chain
-                L.wait_lane(2, 0)
-                if multi:
-                    yield ("D1",), True
-                self.optim_D.step_partial(d1_params, tick=True, last=False)
-                ev_tick = L.record(2)
-                c1r_g = None
-                if cfg.rel or not cfg.skip_dead_real_passes:
-                    c1r_g, _ = rt["D1"].forward([x, m], True, packed=pk_xm)       # cgan.py:321
-                c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)         # cgan.py:322
+                ev_tick, c1r_g, c1f, w1f = None, None, None, None
+                if self._early_d1:
+                    L.wait_lane(2, 0)
+                    if multi:
+                        yield ("D1",), True
+                    self.optim_D.step_partial(d1_params, tick=True, last=False)
+                    ev_tick = L.record(2)
+                    if cfg.rel or not cfg.skip_dead_real_passes:
+                        c1r_g, _ = rt["D1"].forward([x, m], True, packed=pk_xm)       # cgan.py:321
+                    c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)         # cgan.py:322
             share = rt["G2"].convs[0].thin == "cin" and rt["D1"].convs[0].thin == "cin"
             yp, wg2 = rt["G2"].forward([x, mp], True, packed=pk_xmp if share else None)
             pk_xmpyp = rt["D2"].pack_sources([x, mp, yp])
@@ -354,21 +360,33 @@ class STCGANEngine:
                     L.wait_lane(3, 1)
                 d_fake("D2", [x, mp, yp], pk_xmpyp, cfg.lambda3, 1, c2r, w2r)
         # D2's bucket is the one on the critical path: D2 fake chain -> all-reduce -> its Adam share -> G-phase D2 forwards
-        L.join_lanes((1, 3))
         self.last = dict(m_pred=mp, y_pred=yp)
         del w1r, w2r
-        if multi:
-            yield ("D2",), True
-        if ev_tick is not None:
-            torch.cuda.current_stream().wait_event(ev_tick)      # the step counter advanced with D1's share
-        self.optim_D.step_partial(d2_params, tick=False, last=True)           # cgan.py:305
+        if self._early_d1:
+            L.join_lanes((1, 3))
+            if multi:
+                yield ("D2",), True
+            if ev_tick is not None:
+                torch.cuda.current_stream().wait_event(ev_tick)      # the step counter advanced with D1's share
+            self.optim_D.step_partial(d2_params, tick=False, last=True)           # cgan.py:305
+        else:
+            L.join()
+            if multi:
+                yield ("D1", "D2"), True
+            self.optim_D.step()                                                   # cgan.py:305
         # ================= G phase (cgan.py:316-351) =================
         rt["G1"].zero_grads(); rt["G2"].zero_grads()
         # D2's two forward passes with the updated discriminator (cgan.py:323-324) sit on the step's critical path.  They are
         # independent except for the ORDER of their BatchNorm running-statistics updates (real first), so the real pass runs
         # on a lane next to the fake pass, whose updates are deferred and applied after the join (same arithmetic, same order)
-        c2r_g, overlap_real = None, bool(L.streams) and os.environ.get("STCGAN_OVERLAP_REAL", "1") != "0"
+        c2r_g, overlap_real = None, self._overlap_real
         need_real = cfg.rel or not cfg.skip_dead_real_passes
+        if not self._early_d1:
+            L.fork()
+            with L.lane(0):
+                if need_real:
+                    c1r_g, _ = rt["D1"].forward([x, m], True, packed=pk_xm)       # cgan.py:321
+                c1f, w1f = rt["D1"].forward([x, mp], True, packed=pk_xmp)         # cgan.py:322
         if need_real and overlap_real:
             L.lane_wait(1)
             with L.lane(1):
@@ -416,7 +434,8 @@ class STCGANEngine:
         split = bool(L.streams)
         cap = int(os.environ.get("STCGAN_ADAM_OVERLAP_CTAS", "148"))
         g2_params = list(self.nets["G2"].parameters())
-        if split:
+        early = split and self._adam_early
+        if early:
             L.fork()
             with L.lane(0):
                 if multi:
@@ -426,18 +445,28 @@ class STCGANEngine:
             rt["G1"].backward(wg1, dm, False, part="dec")
         if multi:
             yield ("G1.ups",), False
-        if split:
+        if early:
             L.lane_wait(0)                                    # the lane sees the decoder half's weight gradients
             with L.lane(0):
                 if multi:
                     yield (), False, ("G1.ups",)
                 self.optim_G.step_partial(self._g1_ups, tick=False, last=False, max_ctas=cap)
+        elif split:                                           # round-1 schedule: G2's share under the encoder half only
+            L.fork()
+            with L.lane(0):
+                if multi:
+                    yield (), False, ("G2",)
+                self.optim_G.step_partial(g2_params, tick=True, last=False, max_ctas=cap)
         with self._critical():
             rt["G1"].backward(wg1, dm, False, part="enc")
         if split:
             L.join()
             if multi:
-                yield ("G1.rest",), True
+                yield ("G1.rest",), (True if early else False), (("G1.ups",) if not early else ())
+            if not early:
+                self.optim_G.step_partial(self._g1_ups, tick=False, last=False)   # under the last bucket's all-reduce
+                if multi:
+                    yield (), True
             self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
         else:
             if multi:
@@ -661,3 +690,66 @@ def infer_u8(G1, G2, x_u8, out_m=None, out_y=None):
     if out_y is not None:
         out_y.copy_(y8, non_blocking=True)
     return m8, y8
+
+
+class InferencePipeline:
+    """CGAN.infer over a stream of host batches (src/cgan.py:426-460) with the transfers off the critical path: while batch i
+    runs G1 -> G2 on the compute stream, batch i+1's decoded uint8 images travel host -> device and batch i-1's uint8 results
+    travel device -> host on two copy streams (double-buffered pinned / device slots).  `submit(x_u8)` returns the PREVIOUS
+    batch's `(m_u8 [N,H,W,1], y_u8 [N,H,W,3])` as pinned host tensors (None on the first call), `flush()` the last one's;
+    a returned pair stays valid until the second next `submit`."""
+
+    def __init__(self, G1, G2):
+        self.G1, self.G2 = G1, G2
+        self.dev = next(G1.parameters()).device
+        self.cin, self.cout = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        self.slots = [dict(primed=False) for _ in range(2)]
+        self.k = 0
+
+    def _slot(self, i, x_u8):
+        sl = self.slots[i]
+        if sl.get("shape") != tuple(x_u8.shape):
+            n, h, w, _ = x_u8.shape
+            sl.update(shape=tuple(x_u8.shape), x8=torch.empty(x_u8.shape, dtype=torch.uint8, device=self.dev),
+                      out_m=torch.empty((n, h, w, 1), dtype=torch.uint8).pin_memory(),
+                      out_y=torch.empty((n, h, w, self.G2.out_channels), dtype=torch.uint8).pin_memory(),
+                      ready=torch.cuda.Event(), consumed=torch.cuda.Event(), computed=torch.cuda.Event(), done=torch.cuda.Event(),
+                      primed=False, keep=None)
+        return sl
+
+    @torch.no_grad()
+    def submit(self, x_u8):
+        if x_u8.is_cuda or x_u8.dtype != torch.uint8 or x_u8.dim() != 4:
+            raise ValueError("submit expects a (pinned) host uint8 [N,H,W,3] batch")
+        i = self.k % 2
+        sl, main = self._slot(i, x_u8), torch.cuda.current_stream(self.dev)
+        if sl["primed"]:
+            sl["done"].synchronize()                   # this slot's previous results have left the device (host may reuse out_*)
+            self.cin.wait_event(sl["consumed"])
+        with torch.cuda.stream(self.cin):
+            sl["x8"].copy_(x_u8, non_blocking=True)
+            sl["ready"].record(self.cin)
+        main.wait_event(sl["ready"])
+        x = ops.u8_to_nchw(sl["x8"])
+        sl["consumed"].record(main)
+        _, _, m8, y8 = infer(self.G1, self.G2, x)
+        sl["computed"].record(main)
+        self.cout.wait_event(sl["computed"])
+        with torch.cuda.stream(self.cout):
+            sl["out_m"].copy_(m8, non_blocking=True)
+            sl["out_y"].copy_(y8, non_blocking=True)
+            sl["done"].record(self.cout)
+        m8.record_stream(self.cout); y8.record_stream(self.cout)
+        sl["primed"] = True
+        self.k += 1
+        return self._result((self.k - 2) % 2) if self.k >= 2 else None
+
+    def _result(self, j):
+        sl = self.slots[j]
+        if not sl.get("primed"):
+            return None
+        sl["done"].synchronize()
+        return sl["out_m"], sl["out_y"]
+
+    def flush(self):
+        return self._result((self.k - 1) % 2) if self.k >= 1 else None

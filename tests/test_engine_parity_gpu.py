@@ -129,8 +129,8 @@ def test_cuda_graph_replay_equals_eager(cuda, lib, states, batch, size):
         frac_ab, frac_ac = (d_ab > 0.5 * lr).float().mean().item(), (d_ac > 0.5 * lr).float().mean().item()
         assert frac_ab <= max(3 * frac_ac, 0.01), (n, frac_ab, frac_ac)
         print(f"  {n}: fraction of parameters more than lr/2 apart after 4 steps: eager-graph {frac_ab:.2e}, eager-eager {frac_ac:.2e}")
-        for k in ba[n]:
-            assert rel_err(bb[n][k], ba[n][k]) < 1e-2, (n, k)
+        for k in ba[n]:         # BatchNorm buffers: same yardstick (the trajectories of two runs drift apart, see above)
+            assert rel_err(bb[n][k], ba[n][k]) < max(1e-2, 3 * rel_err(bc[n][k], ba[n][k])), (n, k)
     print(f"B={batch} {size}^2: loss |eager-graph| {float((la[:, :6] - lb[:, :6]).abs().max()):.2e} (eager-eager {noise_l:.2e})")
 
 

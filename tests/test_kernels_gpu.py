@@ -536,5 +536,5 @@ def test_thin_first_layer_with_two_activations(cuda, lib, cin, n, h, w_):
     torch.cuda.synchronize()
     ref = F.conv2d(x.double(), _round(w, "bf16").double(), None, 2, 1)
     assert rel_err(_nchw(a), F.leaky_relu(ref, 0.2)) < 6e-3 and rel_err(_nchw(cat[..., :64]), F.relu(ref)) < 6e-3
-    assert torch.equal(a, F.leaky_relu(y.float(), 0.2).to(torch.bfloat16)) and torch.equal(cat[..., :64], F.relu(y))
+    assert torch.equal(cat[..., :64], F.relu(y))             # (ReLU commutes with the bf16 rounding; 0.2 * v does not)
     assert float(cat[..., 64:].abs().max()) == 0.0
