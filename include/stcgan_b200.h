@@ -322,6 +322,19 @@ int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t
  * transpose (src/dataset.py:152: (s.transpose(2,0,1) - 0.5) * 2): uint8 [N,H,W,C] -> float32 [N,C,H,W], bit-exact with
  * numpy's float32 arithmetic, so the host only ships the decoded uint8 images (4x fewer H2D bytes). */
 int stcgan_u8_hwc_to_nchw_f32(const uint8_t* in_nhwc, int N, int H, int W, int C, float* out_nchw, void* stream);
+/* The reference's training augmentation on the GPU, fused with the transform above (src/transform.py:57-156 as composed by
+ * src/cgan.py:105-110: RandomScale -> RandomRotate -> RandomHorizontalFlip -> RandomCrop, applied to utils.uint2float(image)):
+ * uint8 [N,H,W,C] (C = 1 or 3) -> float32 [N,C,crop_h,crop_w] in [-1,1].  The host draws the random numbers (in the
+ * reference's order: stcgan_b200.augment.sample_params) and passes, per image, the INVERSES of the two cv.warpAffine
+ * matrices in float64 (formed like cv::warpAffine forms them), the flip flag and the crop offsets; both warps are bilinear
+ * with a zero border, the second one resampling the first one's output as in the reference.  crop <= image size only. */
+typedef struct stcgan_aug_sample {
+  double scale_inv[6];   /* row-major 2x3: source position = scale_inv * (x, y, 1) */
+  double rot_inv[6];
+  int32_t flip, row_off, col_off, identity;   /* identity != 0: scale == 1 and angle == 0 */
+} stcgan_aug_sample;
+int stcgan_augment_u8(const uint8_t* img_nhwc, int N, int H, int W, int C, const stcgan_aug_sample* dev_samples,
+                      int crop_h, int crop_w, float* out_nchw, void* stream);
 /* plain float2uint on a flat array (known-answer tests) */
 int stcgan_float2uint(const float* in, int64_t n, uint8_t* out, void* stream);
 

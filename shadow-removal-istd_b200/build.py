@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "stcgan_b200", "libstcgan_b200.so")
 STAMP = OUT + ".stamp"
-SOURCES = ["api.cu", "tapconv_ffma.cu", "tapconv_tc.cu", "bn_act.cu", "misc.cu", "thin_col2im.cu"]
+SOURCES = ["api.cu", "tapconv_ffma.cu", "tapconv_tc.cu", "bn_act.cu", "misc.cu", "thin_col2im.cu", "augment.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(HERE, "..", "include", "stcgan_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -34,6 +34,7 @@ int pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void
 int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st);
 int bn_finalize(const double* acc, long long P, int C, const float* gamma, const float* beta, float* rmean, float* rvar,
                 float momentum, float eps, int training, float* mean_invstd, float* scale_shift, cudaStream_t st);
+int augment_u8(const uint8_t* img, int N, int H, int W, int C, const void* samples, int CH, int CW, float* out, cudaStream_t st);
 int bn_running_update(const double* acc, long long count, int C, float* rmean, float* rvar, float momentum, cudaStream_t st);
 int bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, int HC, int WC,
                  void* o1, int ld1, int act1, void* o2, int ld2, int act2, cudaStream_t st);
@@ -338,6 +339,12 @@ int stcgan_adam_tile(void) { return 32; }
 int stcgan_float2uint_hwc(const float* nchw, int N, int C, int H, int W, uint8_t* out_nhwc, void* stream) {
   STCGAN_REQUIRE(nchw && out_nhwc);
   return float2uint_hwc(nchw, N, C, H, W, out_nhwc, as_stream(stream));
+}
+
+int stcgan_augment_u8(const uint8_t* img_nhwc, int N, int H, int W, int C, const stcgan_aug_sample* dev_samples,
+                      int crop_h, int crop_w, float* out_nchw, void* stream) {
+  STCGAN_REQUIRE(img_nhwc && dev_samples && out_nchw && N >= 0 && H > 0 && W > 0 && crop_h > 0 && crop_w > 0);
+  return augment_u8(img_nhwc, N, H, W, C, dev_samples, crop_h, crop_w, out_nchw, as_stream(stream));
 }
 
 int stcgan_u8_hwc_to_nchw_f32(const uint8_t* in_nhwc, int N, int H, int W, int C, float* out_nchw, void* stream) {

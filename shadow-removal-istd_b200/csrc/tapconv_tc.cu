@@ -95,7 +95,10 @@ struct TapGemmSmem {
   static_assert(MT == 1 || (BN >= 64 && MT * BN <= 512), "two accumulators need 2 x BN TMEM columns");
 };
 
-template <int BN, int STAGES, int MT = 1, int NI = 1>
+// EP = extended epilogue (per-channel scale, second output; inference only): a separate instantiation, so that the training
+// kernels keep the plain epilogue (the generalised one cost 3-7 % on every launch and 33 % on the epilogue-bound thin-K
+// persistent kernel when it was a run-time switch: registers and a second loop level around the TMEM reads)
+template <int BN, int STAGES, int MT = 1, int NI = 1, bool EP = false>
 __global__ void __launch_bounds__(NI == 2 ? 224 : 192)
 tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
   pdl_trigger();
@@ -261,9 +264,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
         }
       }
     } else if (P.part_out == nullptr) {
+      constexpr int PITCH = BN * 2 + 16;
+      if constexpr (EP) {
       // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced.  With a second
       // output (P.y2) the accumulators are read from TMEM a second time and go through the same staging rows.
-      constexpr int PITCH = BN * 2 + 16;
       const float* bias = P.bias;
       const float* scale = P.ep_scale;
       const int npass = P.y2 ? 2 : 1;
@@ -301,6 +305,62 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemmParams P) {
             for (int e = 0; e < 4; ++e) {
               float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
               if (scale) { f0 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e); f1 *= __ldg(scale + n_col0 + c0 + v * 8 + 2 * e + 1); }
+              if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+              f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              w[e] = valid ? *reinterpret_cast<const uint32_t*>(&h) : 0u;     // rows outside the tensor count as zeros below
+            }
+            st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
+          }
+        }
+        __syncwarp();
+        if (threadIdx.x == 64) DBG_T(7);
+        constexpr int LPR = BN * 2 / 16;     // lanes per output row (16-byte pieces)
+        constexpr int RPI = 32 / LPR;        // rows per warp-wide store instruction
+        const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+        const uint32_t wbase = smem_u32(smem) + (uint32_t)(mt * TC_BM + q * 32) * PITCH;
+#pragma unroll 4
+        for (int i = 0; i < 32; i += RPI) {
+          const int rr = i + lane / LPR;
+          const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+          if (pr) {
+            const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * PITCH + (lane % LPR) * 16);
+            *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+          }
+        }
+      }
+      }
+      } else {
+      // stage the bf16 tile in (now idle) pipeline smem, one row per thread, then store whole rows coalesced
+      const float slope = act_slope(P.act);
+      const float* bias = P.bias;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt > 0) {                           // rows 128.. of the tile live in the second accumulator
+          row = mt * TC_BM + q * 32 + lane;
+          wl = row % P.wt; hl = (row / P.wt) % P.ht; nl = row / (P.wt * P.ht);
+          a = a0 + hl; b = b0 + wl; n = n0 + nl;
+          oy = a * P.ostride + P.oy0[cls]; ox = b * P.ostride + P.ox0[cls];
+          valid = n < P.N && oy < P.OH && ox < P.OW;
+          out = P.y + ((long long)(n * P.OH + oy) * P.OW + ox) * P.ldy + n_col0;
+        }
+        const uint32_t stg = smem_u32(smem) + (uint32_t)row * PITCH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * BN + c0), r);
+          if constexpr (NI == 2) {           // add the second issuer's accumulator
+            uint32_t r2[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(MT * BN + mt * BN + c0), r2);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
               if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
               f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
               const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
@@ -423,7 +483,7 @@ struct PersistSmem {
 };
 
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool EP = false>
 __global__ void __launch_bounds__(192, 1)
 tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tiles, int n_tiles, int total_tiles) {
   pdl_trigger();
@@ -521,7 +581,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
     const int wl = row % P.wt, hl = (row / P.wt) % P.ht, nl = row / (P.wt * P.ht);
     const float slope = act_slope(P.act);
     const float* bias = P.bias;
-    const float* scale = P.ep_scale;
+    [[maybe_unused]] const float* scale = P.ep_scale;
     const uint32_t stg = smem_u32(smem + SM::STAGING_OFFSET) + (uint32_t)row * SM::PITCH;
     const uint32_t wbase = smem_u32(smem + SM::STAGING_OFFSET) + (uint32_t)(q * 32) * SM::PITCH;
     constexpr int LPR = BN * 2 / 16;
@@ -537,6 +597,7 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
       const uint32_t buf = li & 1u;
       mbar_wait_warp(&tmem_full[buf], (li >> 1) & 1u, lane);
       tc_fence_after();
+      if constexpr (EP) {
       const int npass = P.y2 ? 2 : 1;                 // second output: the accumulators are read twice (see TapGemmParams)
 #pragma unroll 1
       for (int op = 0; op < npass; ++op) {
@@ -580,6 +641,41 @@ tapgemm_tc_persistent_kernel(const __grid_constant__ TapGemmParams P, int m_tile
             *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
           }
         }
+      }
+      } else {
+      __syncwarp();                                   // previous tile's row stores of this warp have read the staging rows
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c0, r);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+            if (bias) { f0 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e); f1 += __ldg(bias + n_col0 + c0 + v * 8 + 2 * e + 1); }
+            f0 = act_piecewise(f0, slope); f1 = act_piecewise(f1, slope);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+            w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          st_shared_v4(stg + c0 * 2 + v * 16, w[0], w[1], w[2], w[3]);
+        }
+      }
+      // all TMEM reads of this buffer are complete (tcgen05.wait::ld inside tmem_ld): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      const unsigned long long myp = valid ? reinterpret_cast<unsigned long long>(out) : 0ull;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += RPI) {
+        const int rr = i + lane / LPR;
+        const unsigned long long pr = __shfl_sync(0xffffffffu, myp, rr);
+        if (pr) {
+          const uint4 v = ld_shared_v4(wbase + (uint32_t)rr * SM::PITCH + (lane % LPR) * 16);
+          *reinterpret_cast<uint4*>(pr + (lane % LPR) * 16) = v;
+        }
+      }
       }
     }
   }
@@ -1024,6 +1120,19 @@ static int launch_tapgemm(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
 template <int BN, int STAGES, int MT, int NI>
 static int launch_tapgemm_raw(const TapGemmParams& P, dim3 grid, cudaStream_t st) {
   using SM = TapGemmSmem<BN, STAGES, MT, NI>;
+  if constexpr (NI == 1 && BN >= 64) {
+    if (P.ep_scale || P.y2) {          // extended epilogue: its own instantiation (see tapgemm_tc_kernel)
+      static bool configured_ep = false;
+      if (!configured_ep) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, MT, NI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        configured_ep = true;
+      }
+      launch_k(tapgemm_tc_kernel<BN, STAGES, MT, NI, true>, grid, 192, SM::TOTAL, st, P);
+      return finish_launch();
+    }
+  }
+  if (P.ep_scale || P.y2) return STCGAN_EUNSUPPORTED;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, MT, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
@@ -1038,15 +1147,25 @@ template <int BN, int STAGES>
 static int launch_tapgemm_persistent(const TapGemmParams& P, int m_tiles, int n_tiles, int nclass, cudaStream_t st,
                                      int ctas_per_sm = 1) {
   using SM = PersistSmem<BN, STAGES>;
+  const int total = m_tiles * n_tiles * nclass;
+  const int cap = 148 * ctas_per_sm;
+  const int grid = total < cap ? total : cap;
+  if (P.ep_scale || P.y2) {            // extended epilogue: its own instantiation (see tapgemm_tc_kernel)
+    static bool configured_ep = false;
+    if (!configured_ep) {
+      cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_persistent_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+      if (e != cudaSuccess) return (int)e;
+      configured_ep = true;
+    }
+    launch_k(tapgemm_tc_persistent_kernel<BN, STAGES, true>, grid, 192, SM::TOTAL, st, P, m_tiles, n_tiles, total);
+    return finish_launch();
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_persistent_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  const int total = m_tiles * n_tiles * nclass;
-  const int cap = 148 * ctas_per_sm;
-  const int grid = total < cap ? total : cap;
   launch_k(tapgemm_tc_persistent_kernel<BN, STAGES>, grid, 192, SM::TOTAL, st, P, m_tiles, n_tiles, total);
   return finish_launch();
 }

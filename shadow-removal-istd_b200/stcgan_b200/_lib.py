@@ -37,6 +37,11 @@ class AdamTensor(C.Structure):
                 ("n", C.c_int64), ("d0", C.c_int32), ("d1", C.c_int32), ("p1", C.c_void_p), ("p2", C.c_void_p)]
 
 
+class AugSample(C.Structure):
+    _fields_ = [("scale_inv", C.c_double * 6), ("rot_inv", C.c_double * 6), ("flip", C.c_int32), ("row_off", C.c_int32),
+                ("col_off", C.c_int32), ("identity", C.c_int32)]
+
+
 _i, _p, _f, _i64 = C.c_int, C.c_void_p, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); every symbol declared in include/stcgan_b200.h is listed here
@@ -84,6 +89,7 @@ SIGNATURES = {
     "stcgan_float2uint_hwc": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_float2uint": (_i, [_p, _i64, _p, _p]),
     "stcgan_u8_hwc_to_nchw_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "stcgan_augment_u8": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

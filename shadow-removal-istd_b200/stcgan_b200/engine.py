@@ -381,6 +381,10 @@ class STCGANEngine:
         # on a lane next to the fake pass, whose updates are deferred and applied after the join (same arithmetic, same order)
         c2r_g, overlap_real = None, self._overlap_real
         need_real = cfg.rel or not cfg.skip_dead_real_passes
+        # the thin layers' packed weights are re-derived from the updated parameters HERE, on the stream every consumer is
+        # ordered behind -- not lazily inside whichever forward pass happens to run first (found with tools/noise_check.py: with
+        # the real pass on a lane the fake pass could read D2's first / last layer weights while they were being re-packed)
+        rt["D2"].ensure_packed()
         if not self._early_d1:
             L.fork()
             with L.lane(0):

@@ -538,3 +538,27 @@ def test_thin_first_layer_with_two_activations(cuda, lib, cin, n, h, w_):
     assert rel_err(_nchw(a), F.leaky_relu(ref, 0.2)) < 6e-3 and rel_err(_nchw(cat[..., :64]), F.relu(ref)) < 6e-3
     assert torch.equal(cat[..., :64], F.relu(y))             # (ReLU commutes with the bf16 rounding; 0.2 * v does not)
     assert float(cat[..., 64:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case,kw", [("full", dict(scale=0.05, angle=15, flip_prob=0.5)),
+                                     ("flipcrop", dict(scale=None, angle=None, flip_prob=0.5))])
+def test_gpu_augmentation_matches_reference_golden(cuda, lib, case, kw):
+    """stcgan_augment_u8 (RandomScale -> RandomRotate -> RandomHorizontalFlip -> RandomCrop + the dataset transform, SURVEY
+    8f-2) against vectors produced by the reference's transform classes on OpenCV (tests/golden/make_golden_augment.py) and
+    against the CPU restatement: BIT-EXACT (cv::warpAffine works in fixed-point source positions and a fixed float32 expression)."""
+    import os
+    import augment_oracle as AO
+    from conftest import ROOT
+    from stcgan_b200 import augment as A
+    vec = np.load(os.path.join(ROOT, "tests", "golden", "augment_vectors.npz"))
+    h, w, crop, n = (int(v) for v in vec["meta"])
+    np.random.seed(42)
+    params = A.sample_params(np.random, n, h, w, crop=crop, **kw)
+    for key in ("img", "matte"):
+        u8 = torch.from_numpy(vec[f"{case}/{key}_u8"]).to(cuda).contiguous()
+        got = A.augment_u8(u8, params, crop).cpu().numpy()
+        want = vec[f"{case}/{key}_out"]
+        mine = np.stack([AO.augment(vec[f"{case}/{key}_u8"][i], params[i], crop) for i in range(n)])
+        assert got.shape == want.shape
+        assert np.array_equal(mine, want)       # the CPU restatement is pinned to the reference + OpenCV
+        assert np.array_equal(got, want), float(np.abs(got - want).max())      # and the kernel reproduces it bit for bit

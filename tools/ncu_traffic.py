@@ -33,8 +33,8 @@ def main(path, out):
     fam = collections.defaultdict(lambda: dict(launches=0, dram_read=0.0, dram_write=0.0, seconds=0.0, tensor_pct_time=0.0))
     for d in per.values():
         n = d["name"]
-        key = ("conv_tc" if n.startswith(("stcgan::tapgemm_tc", "stcgan::tapwgrad_tc", "tapgemm_tc", "tapwgrad_tc")) else
-               "thin" if "pixgemm" in n or "persistent" in n else
+        key = ("thin" if "pixgemm" in n or "persistent" in n else
+               "conv_tc" if ("tapgemm_tc_kernel" in n or "tapwgrad_tc_kernel" in n) else
                "batchnorm" if "bn_" in n else
                "adam" if "adam" in n else "other")
         a = fam[key]
