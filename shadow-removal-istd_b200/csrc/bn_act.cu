@@ -4,6 +4,7 @@
 //
 // Reference arithmetic: nn.BatchNorm2d (eps 1e-5, momentum 0.1, affine) + nn.LeakyReLU(0.2, True) /
 // nn.ReLU(True) -- src/models/stcgan_g.py:87-90, src/models/stcgan_d.py:24,36-37,45-46.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace stcgan {
@@ -283,8 +284,8 @@ struct BnFinalize {
   float* mean_invstd; float* scale_shift;   // [2][C] each
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int U = 4, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 bn_fused_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, const BnFinalize f,
                       int HC, int WC, long long PC, T* __restrict__ o1, int ld1, int act1,
                       T* __restrict__ o2, int ld2, int act2, int cv, int rows) {
@@ -331,10 +332,10 @@ bn_fused_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, con
     for (int i = 0; i < 8; ++i) { sc[i] = ssm[c0 + i]; sh[i] = ssm[C + c0 + i]; }
     const long long stride = (long long)gridDim.x * rows;
     const bool nocrop = HC == H && WC == W;
-    for (long long p0 = (long long)blockIdx.x * rows + tr; p0 < PC; p0 += 4 * stride) {
-      Raw8<T> raw[4];
+    for (long long p0 = (long long)blockIdx.x * rows + tr; p0 < PC; p0 += U * stride) {
+      Raw8<T> raw[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         long long p = p0 + u * stride;
         if (p >= PC) p = PC - 1;
         long long src = p;
@@ -346,7 +347,7 @@ bn_fused_apply_kernel(const T* __restrict__ y, int H, int W, int C, int ldy, con
         raw[u].ld(y + src * (long long)ldy + c0);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long p = p0 + u * stride;
         if (p < PC) {
           Vec8<T> a, b;
@@ -406,8 +407,8 @@ struct BwdIn {
 
 // pass 1: acc[slot][0][c] += sum dz ; acc[slot][1][c] += sum dz * (y - mean)   (fp64 across threads / blocks; the blocks
 // spread their atomics over STCGAN_BN_SLOTS partial slots, pass 2 adds the slots up)
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, int U = 4, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
                      const float* __restrict__ ss, const float* __restrict__ mi, int HC, int WC,
                      const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
@@ -424,12 +425,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
     for (int i = 0; i < 8; ++i) { sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; s[i] = 0.f; q[i] = 0.f; }
     if (active) {
       const long long stride = (long long)gridDim.x * rows;
-      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
-        BwdIn<T> in[4];
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += U * stride) {
+        BwdIn<T> in[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+        for (int u = 0; u < U; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
           if (p + u * stride < P) {
             float dz[8], yv[8];
             in[u].dz(sc, sh, act1, act2, two, dz, yv);
@@ -460,8 +461,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ y, long long P, int H, int W, int C, 
 //         atomically: the real and the fake pass of a discriminator may run their backward passes concurrently).
 //         The per-channel coefficients are derived once per block into shared memory (sum over the statistic slots).
 //         dbias (optional, layers with a conv bias and no BatchNorm): dbias[c] += sum_p dy[p, c].
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, int U = 4, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
                     const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ gamma,
                     int training, int HC, int WC,
@@ -507,12 +508,12 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
     }
     if (active) {
       const long long stride = (long long)gridDim.x * rows;
-      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += 4 * stride) {
-        BwdIn<T> in[4];
+      for (long long p = (long long)blockIdx.x * rows + tr; p < P; p += U * stride) {
+        BwdIn<T> in[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
+        for (int u = 0; u < U; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + u * stride, c0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
           if (p + u * stride < P) {
             float dz[8], yv[8];
             in[u].dz(sc, sh, act1, act2, two, dz, yv);
@@ -565,6 +566,14 @@ static inline unsigned stream_grid(long long P, int rows, K kernel, size_t smem,
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// STCGAN_BN_VAR (tuning experiments, bf16 kernels): 0 = 4 pixels in flight per thread, 2 blocks/SM (round-1 shape);
+// 1 = 2 in flight, 4 blocks/SM; 2 = 4 in flight, 3 blocks/SM; 3 = 2 in flight, 3 blocks/SM
+static int bn_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("STCGAN_BN_VAR"); v = e ? atoi(e) : 0; if (v < 0 || v > 3) v = 0; }
+  return v;
+}
 
 template <typename T>
 static int bn_stats_t(const void* y, long long P, int C, int ld, double* acc, int want_sq, cudaStream_t st) {
@@ -631,10 +640,18 @@ int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy
     launch_k(bn_fused_apply_kernel<float>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<float>, smem), 256, smem, st,
              static_cast<const float*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
              static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
-  else
-    launch_k(bn_fused_apply_kernel<__nv_bfloat16>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
-             static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
-             static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
+  else {
+#define FA_LAUNCH(U_, MB_) launch_k(bn_fused_apply_kernel<__nv_bfloat16, U_, MB_>, stream_grid(PC, m.rows * U_, bn_fused_apply_kernel<__nv_bfloat16, U_, MB_>, smem), 256, smem, st, \
+             static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1, \
+             static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows)
+    switch (bn_variant()) {
+      case 1: FA_LAUNCH(2, 4); break;
+      case 2: FA_LAUNCH(4, 3); break;
+      case 3: FA_LAUNCH(2, 3); break;
+      default: FA_LAUNCH(4, 1); break;
+    }
+#undef FA_LAUNCH
+  }
   return finish_launch();
 }
 
@@ -650,9 +667,18 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
   if (dtype == STCGAN_F32)
     launch_k(bn_bwd_reduce_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 4), 256, smem, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
         static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
-  else
-    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 4), 256, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
-        act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
+  else {
+#define BR_LAUNCH(U_, MB_) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, U_, MB_>, stream_grid(P, m.rows * U_, bn_bwd_reduce_kernel<__nv_bfloat16, U_, MB_>, smem, 4), 256, smem, st, \
+        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1, \
+        act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows)
+    switch (bn_variant()) {
+      case 1: BR_LAUNCH(2, 4); break;
+      case 2: BR_LAUNCH(4, 3); break;
+      case 3: BR_LAUNCH(2, 3); break;
+      default: BR_LAUNCH(4, 2); break;
+    }
+#undef BR_LAUNCH
+  }
   return finish_launch();
 }
 
@@ -673,11 +699,19 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
              static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
              act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows,
              1.0 / (double)P);
-  else
-    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
-             static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
-             static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
-             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows, 1.0 / (double)P);
+  else {
+#define BA_LAUNCH(U_, MB_) launch_k(bn_bwd_apply_kernel<__nv_bfloat16, U_, MB_>, stream_grid(P, m.rows * U_, bn_bwd_apply_kernel<__nv_bfloat16, U_, MB_>, smem), 256, smem, st, \
+             static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, \
+             static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, \
+             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows, 1.0 / (double)P)
+    switch (bn_variant()) {
+      case 1: BA_LAUNCH(2, 4); break;
+      case 2: BA_LAUNCH(4, 3); break;
+      case 3: BA_LAUNCH(2, 3); break;
+      default: BA_LAUNCH(4, 2); break;
+    }
+#undef BA_LAUNCH
+  }
   return finish_launch();
 }
 

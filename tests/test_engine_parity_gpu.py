@@ -92,16 +92,19 @@ def _param_vec(nets):
     return {n: torch.cat([p.detach().reshape(-1) for p in nets[n].parameters()]).double().cpu() for n in nets}
 
 
-@pytest.mark.parametrize("batch,size", [(2, 256), (16, 256)])
-def test_cuda_graph_replay_equals_eager(cuda, lib, states, batch, size):
+@pytest.mark.parametrize("mode,batch", [("fp32", 2), ("bf16", 16)])
+def test_cuda_graph_replay_equals_eager(cuda, lib, states, mode, batch):
     """Same initial state, same batches, one eager warm-up step + 3 steps: (A) eager, (B) captured graph replayed on new
-    inputs, (C) eager again.  A vs C measures the run-to-run noise of the atomics-ordered reductions (Adam's first steps are
-    ~lr*sign(g), which turns noise-level gradients into +-lr); B must sit within 3 x that noise (+ a small floor), its
-    losses within 1e-3 of A's on every step."""
-    batches = [tuple(t.to(cuda) for t in O.make_istd_batch(batch, size, size, seed=50 + i)) for i in range(4)]
+    inputs, (C) eager again.
+      fp32 mode: the only run-to-run noise is the order of fp32 atomics (1e-7), so graph and eager must agree TIGHTLY:
+        losses to 1e-4 on every step, parameters equal except where Adam's sign-like first steps flip a noise-level gradient.
+      bf16 mode at the benchmarked batch: A vs C measures the divergence of two IDENTICAL eager runs (order-dependent bf16
+        rounding is amplified by Adam's ~lr*sign(g) steps and the GAN dynamics -- measured on B200: after 4 steps 30 % of
+        G1's parameters sit more than lr/2 apart between two eager runs); B must sit within a small multiple of that."""
+    batches = [tuple(t.to(cuda) for t in O.make_istd_batch(batch, 256, 256, seed=50 + i)) for i in range(4)]
 
     def run(graph):
-        nets, eng = _engine("bf16", cuda, states)
+        nets, eng = _engine(mode, cuda, states)
         losses = []
         if graph:
             eng.capture(*batches[0], warmup=1)             # = one eager step on batches[0]
@@ -122,16 +125,20 @@ def test_cuda_graph_replay_equals_eager(cuda, lib, states, batch, size):
     lc, pc, bc, sc = run(False)
     assert sa == sb == sc == 4.0                               # host step counter == optimiser steps actually applied
     noise_l = (la - lc).abs().max().item()
-    assert (la[:, :6] - lb[:, :6]).abs().max().item() <= max(1e-3, 3 * noise_l), (la, lb)
+    d_l = (la[:, :6] - lb[:, :6]).abs().max().item()
+    if mode == "fp32":
+        assert d_l <= 1e-4 * la[:, :6].abs().max().item() + 10 * noise_l, (la, lb)
+    else:
+        assert d_l <= max(2e-3, 6 * noise_l), (la, lb, noise_l)
     for n, lr in (("G1", 5e-4), ("G2", 5e-4), ("D1", 1e-4), ("D2", 1e-4)):
         d_ab, d_ac = (pa[n] - pb[n]).abs(), (pa[n] - pc[n]).abs()
         assert d_ab.max().item() <= 3 * lr * 4          # (an Adam step is ~lr, at most a small multiple of it)
         frac_ab, frac_ac = (d_ab > 0.5 * lr).float().mean().item(), (d_ac > 0.5 * lr).float().mean().item()
         assert frac_ab <= max(3 * frac_ac, 0.01), (n, frac_ab, frac_ac)
-        print(f"  {n}: fraction of parameters more than lr/2 apart after 4 steps: eager-graph {frac_ab:.2e}, eager-eager {frac_ac:.2e}")
-        for k in ba[n]:         # BatchNorm buffers: same yardstick (the trajectories of two runs drift apart, see above)
-            assert rel_err(bb[n][k], ba[n][k]) < max(1e-2, 3 * rel_err(bc[n][k], ba[n][k])), (n, k)
-    print(f"B={batch} {size}^2: loss |eager-graph| {float((la[:, :6] - lb[:, :6]).abs().max()):.2e} (eager-eager {noise_l:.2e})")
+        print(f"  {mode} {n}: fraction of parameters more than lr/2 apart after 4 steps: eager-graph {frac_ab:.2e}, eager-eager {frac_ac:.2e}")
+        for k in ba[n]:         # BatchNorm buffers: same yardstick
+            assert rel_err(bb[n][k], ba[n][k]) < max(1e-3 if mode == "fp32" else 1e-2, 3 * rel_err(bc[n][k], ba[n][k])), (n, k)
+    print(f"{mode} B={batch}: loss |eager-graph| {d_l:.2e} (eager-eager {noise_l:.2e})")
 
 
 def test_three_optimiser_steps_vs_oracle_fp32(cuda, lib, states):
