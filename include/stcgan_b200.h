@@ -217,6 +217,13 @@ int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, 
                           float* running_mean, float* running_var, float momentum, float eps, int training,
                           float* mean_invstd, float* scale_shift, int HC, int WC,
                           void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
+/* training-mode BatchNorm(+activation) backward of a SMALL tensor (N*H*W*C <= 256*512 elements, bf16: the U-Net bottleneck
+ * levels) as ONE single-block launch: reduce, coefficients and apply of the two functions below in one kernel, same
+ * arithmetic.  Returns STCGAN_EUNSUPPORTED for larger tensors / other dtypes (run the two-pass form then).  dgamma / dbeta
+ * are ACCUMULATED into (NULL = skip). */
+int stcgan_bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
+                            const float* mean_invstd, const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1,
+                            const void* g2, int ldg2, int act2, void* dy, int lddy, float* dgamma, float* dbeta, void* stream);
 /* backward, pass 1: dz = g1*act1'(z) + g2*act2'(z) (z = y*scale+shift, zero outside the crop);
  * acc[slot][0][c] += sum dz, acc[slot][1][c] += sum dz*(y-mean)   (fp64; acc is [STCGAN_BN_SLOTS][2][C], caller zeroes;
  * the blocks spread their atomics over the slots) */

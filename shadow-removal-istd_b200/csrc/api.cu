@@ -46,6 +46,9 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
                      const void* g2, int ldg2, int act2, const double* acc, void* dy, int lddy,
                      float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
 int colsum(int dtype, const void* g, long long P, int C, int ld, float* out, cudaStream_t st);
+int bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                     const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
+                     int act2, void* dy, int lddy, float* dgamma, float* dbeta, cudaStream_t st);
 int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy, const double* acc, long long count,
                    const float* gamma, const float* beta, float* rmean, float* rvar, float momentum, float eps, int training,
                    float* mean_invstd, float* scale_shift, int HC, int WC,
@@ -197,6 +200,15 @@ int stcgan_bn_act_apply(int dtype, const void* y, int N, int H, int W, int C, in
                         int HC, int WC, void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream) {
   STCGAN_REQUIRE(dtype_ok(dtype) && y && N >= 0 && H > 0 && W > 0 && HC > 0 && WC > 0);
   return bn_act_apply(dtype, y, N, H, W, C, ldy, scale_shift, HC, WC, out1, ld1, act1, out2, ld2, act2, as_stream(stream));
+}
+
+int stcgan_bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,
+                            const float* mean_invstd, const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1,
+                            const void* g2, int ldg2, int act2, void* dy, int lddy, float* dgamma, float* dbeta, void* stream) {
+  STCGAN_REQUIRE(dtype_ok(dtype) && y && N >= 0 && H > 0 && W > 0 && HC > 0 && WC > 0 && C > 0);
+  if (N == 0) return 0;
+  return bn_act_bwd_small(dtype, y, N, H, W, C, ldy, scale_shift, mean_invstd, gamma, HC, WC, g1, ldg1, act1, g2, ldg2, act2,
+                          dy, lddy, dgamma, dbeta, as_stream(stream));
 }
 
 int stcgan_bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* scale_shift,

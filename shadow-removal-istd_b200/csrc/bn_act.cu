@@ -542,6 +542,88 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// small tensors (the U-Net bottleneck: <= 256 pixels x 512 channels): reduce + apply in ONE single-block launch.  The two-pass
+// form costs two dependent ~7 us launches on tensors of a few hundred KB -- pure latency on the backward pass's critical
+// chain (16 such BatchNorm layers per train step); one 1024-thread block reduces in shared memory, derives the coefficients
+// and applies them (the second read of y / g hits L1/L2).  Same arithmetic as the two-pass kernels: fp32 partial sums per
+// thread, fp64 across the block.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+bn_bwd_small_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
+                    const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ gamma,
+                    int HC, int WC, const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
+                    T* __restrict__ dy, int lddy, float* __restrict__ dgamma, float* __restrict__ dbeta, int cv, int rows,
+                    double invP) {
+  extern __shared__ float sm_small[];       // [2][rows][C] partial sums, then [3][C] coefficients behind them
+  pdl_prologue();
+  const int tc = threadIdx.x % cv, tr = threadIdx.x / cv;
+  const bool active = tr < rows;
+  const bool two = g2 != nullptr;
+  float* rs = sm_small; float* rq = sm_small + rows * C;
+  float* coef = sm_small + 2 * rows * C;    // kA, kB, kC
+  // ---- pass 1: per-thread sums over this thread's pixels, every channel vector this thread owns (C <= cv * 8 * k)
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8], mean[8], s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; mean[i] = mi[c0 + i]; s[i] = 0.f; q[i] = 0.f; }
+    if (active)
+      for (long long p = tr; p < P; p += 2 * rows) {
+        BwdIn<T> in[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + (long long)u * rows, c0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (p + (long long)u * rows < P) {
+            float dz[8], yv[8];
+            in[u].dz(sc, sh, act1, act2, two, dz, yv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s[i] += dz[i]; q[i] = fmaf(dz[i], yv[i] - mean[i], q[i]); }
+          }
+      }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rs[tr * C + c0 + i] = s[i]; rq[tr * C + c0 + i] = q[i]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int r = 0; r < rows; ++r) { a0 += rs[r * C + c]; a1 += rq[r * C + c]; }
+    const float mean = mi[c], invstd = mi[C + c];
+    const float kA = gamma[c] * invstd;
+    const float kC = kA * invstd * invstd * (float)(a1 * invP);
+    coef[c] = kA; coef[C + c] = kA * (float)(a0 * invP) - mean * kC; coef[2 * C + c] = kC;
+    if (dgamma) { atomicAdd(&dgamma[c], (float)(a1 * (double)invstd)); atomicAdd(&dbeta[c], (float)a0); }
+  }
+  __syncthreads();
+  // ---- pass 2: dy = kA*dz - kB - y*kC
+  for (int c0 = tc * VEC; c0 < C; c0 += cv * VEC) {
+    float sc[8], sh[8], kA[8], kB[8], kC[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = ss[c0 + i]; sh[i] = ss[C + c0 + i]; kA[i] = coef[c0 + i]; kB[i] = coef[C + c0 + i]; kC[i] = coef[2 * C + c0 + i];
+    }
+    if (active)
+      for (long long p = tr; p < P; p += 2 * rows) {
+        BwdIn<T> in[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) in[u].load(y, P, H, W, ldy, HC, WC, g1, ldg1, g2, ldg2, p + (long long)u * rows, c0);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (p + (long long)u * rows < P) {
+            float dz[8], yv[8];
+            in[u].dz(sc, sh, act1, act2, two, dz, yv);
+            Vec8<T> o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = fmaf(kA[i], dz[i], -kB[i]) - yv[i] * kC[i];
+            o.store(dy + (p + (long long)u * rows) * lddy + c0);
+          }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 // Grid for a grid-stride streaming kernel: exactly one wave of resident CTAs (148 SMs x occupancy), fewer for small
@@ -712,6 +794,33 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
     }
 #undef BA_LAUNCH
   }
+  return finish_launch();
+}
+
+// training-mode BatchNorm(+activation) backward of a SMALL tensor in one launch; returns STCGAN_EUNSUPPORTED when the tensor
+// is not small (the caller then runs the two-pass form)
+int bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int ldy, const float* ss, const float* mi,
+                     const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
+                     int act2, void* dy, int lddy, float* dgamma, float* dbeta, cudaStream_t st) {
+  const long long P = (long long)N * H * W;
+  if (dtype != STCGAN_BF16 || C % VEC != 0 || C > 1024 || P * C > 256LL * 512 || P < 1) return STCGAN_EUNSUPPORTED;
+  if (!ss || !mi || !gamma || !g1 || !dy || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2) ||
+      !vec_ok(dtype, dy, lddy))
+    return STCGAN_EINVAL;
+  int cv = C / VEC; if (cv > 1024) cv = 1024;
+  int rows = 1024 / cv; if (rows < 1) rows = 1;
+  if ((long long)rows > P) rows = (int)P;
+  const size_t smem = ((size_t)2 * rows * C + 3 * C) * sizeof(float);
+  if (smem > 200 * 1024) return STCGAN_EUNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(bn_bwd_small_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  launch_k(bn_bwd_small_kernel<__nv_bfloat16>, 1, 1024, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi,
+           gamma, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2,
+           static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, cv, rows, 1.0 / (double)P);
   return finish_launch();
 }
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "stcgan_bn_finalize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p]),
     "stcgan_bn_running_update": (_i, [_p, _i64, _i, _p, _p, _f, _p]),
     "stcgan_bn_act_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
+    "stcgan_bn_act_bwd_small": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _i, _p, _p, _p]),
     "stcgan_bn_act_bwd_reduce": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _i, _p, _i, _i, _p, _p]),
     "stcgan_bn_act_bwd_apply": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _i, _i,
                                      _p, _p, _i, _p, _p, _p, _p]),

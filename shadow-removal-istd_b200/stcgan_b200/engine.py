@@ -204,11 +204,14 @@ class STCGANEngine:
         # G2, G1's up-conv weights ("G1.ups"), the rest of G1
         g2_ids = {id(p) for p in G2.parameters()}
         ups_ids = {id(c.weight) for c in self.rt["G1"].ups}
+        deep_ids = {id(c.weight) for c in self.rt["G1"].deep_convs}
         self._g1_ups = [c.weight for c in self.rt["G1"].ups]
         self._g1_rest = [p for p in G1.parameters() if id(p) not in ups_ids]
-        self.optim_G.set_block_order(lambda p: 0 if id(p) in g2_ids else (1 if id(p) in ups_ids else 2))
+        self._g1_deep = [c.weight for c in self.rt["G1"].deep_convs]
+        self._g1_tail = [p for p in G1.parameters() if id(p) not in ups_ids and id(p) not in deep_ids]
+        self.optim_G.set_block_order(lambda p: 0 if id(p) in g2_ids else (1 if id(p) in ups_ids else (2 if id(p) in deep_ids else 3)))
         self.optim_D.set_pack_targets(self.rt["D1"].convs + self.rt["D2"].convs)
-        def bucket(name):                  # "G1" -> whole flat buffer, "G1.ups" / "G1.rest" -> its slices
+        def bucket(name):                  # "G1" -> whole flat buffer, "G1.ups" / "G1.deep" / "G1.tail" / "G1.rest" -> its slices
             net, _, part = name.partition(".")
             return self.rt[net].grad_bucket(part or None)
         self.sync = GradientSync(bucket, process_group)
@@ -461,17 +464,39 @@ class STCGANEngine:
                 if multi:
                     yield (), False, ("G2",)
                 self.optim_G.step_partial(g2_params, tick=True, last=False, max_ctas=cap)
+        # the encoder half completes G1's weight gradients innermost level first: the four 512 x 512 down convs (86 % of what
+        # is left) form the "deep" bucket, which goes on the wire -- and then through Adam, on the lane -- while the outer
+        # levels are still running; only the small "tail" bucket is exchanged and applied after the backward pass
+        deep = {"ev": None}
+
+        def deep_done():                                      # (current stream = the weight-gradient stream)
+            if multi:
+                self._reduce((("G1.deep",), False), self._pending)
+            deep["ev"] = torch.cuda.Event()
+            deep["ev"].record()
+
         with self._critical():
-            rt["G1"].backward(wg1, dm, False, part="enc")
+            rt["G1"].backward(wg1, dm, False, part="enc", on_deep=deep_done if early else None)
+        if early:
+            with L.lane(0):
+                if deep["ev"] is not None:
+                    L.streams[0].wait_event(deep["ev"])
+                if multi:
+                    yield (), False, ("G1.deep",)
+                self.optim_G.step_partial(self._g1_deep, tick=False, last=False, max_ctas=cap)
         if split:
             L.join()
-            if multi:
-                yield ("G1.rest",), (True if early else False), (("G1.ups",) if not early else ())
-            if not early:
+            if early:
+                if multi:
+                    yield ("G1.tail",), True
+                self.optim_G.step_partial(self._g1_tail, tick=False, last=True)
+            else:
+                if multi:
+                    yield ("G1.rest",), False, ("G1.ups",)
                 self.optim_G.step_partial(self._g1_ups, tick=False, last=False)   # under the last bucket's all-reduce
                 if multi:
                     yield (), True
-            self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
+                self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
         else:
             if multi:
                 yield ("G1.ups", "G1.rest"), True            # (blocking: waits for G2's sum as well)
@@ -506,9 +531,9 @@ class STCGANEngine:
         for t in (x, m, y):
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise RuntimeError("train_step expects float32 CUDA tensors")
-        pending = []
+        self._pending = []
         for req in self._step_segments(x.contiguous(), m.contiguous(), y.contiguous()):
-            self._reduce(req, pending)
+            self._reduce(req, self._pending)
         return self.losses
 
     def capture(self, x, m, y, warmup=3):
@@ -529,7 +554,7 @@ class STCGANEngine:
         torch.cuda.synchronize()
         self.optim_D.prepare(); self.optim_G.prepare()
         before = _lib.launch_count()
-        self._graphs, pending = [], []
+        self._graphs, self._pending = [], []
         if self.world > 1 and os.environ.get("STCGAN_NCCL_IN_GRAPH", "1") == "0":
             self.train_step(*self._static)
             self.graph_launches = _lib.launch_count() - before
@@ -538,7 +563,7 @@ class STCGANEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):            # the warm-up stream: per-stream scratch already exists
                 for req in self._step_segments(*self._static):
-                    self._reduce(req, pending)
+                    self._reduce(req, self._pending)
             self._graphs.append(g)
             self.graph_launches = _lib.launch_count() - before
             self._graph = "graph"

@@ -338,11 +338,15 @@ class _NetRuntimeBase:
         self.alloc_grads()
         if name in (None, "all"):
             return self.flat_grad
-        n_ups = getattr(self, "_n_ups", 0)
+        n_ups, n_deep = getattr(self, "_n_ups", 0), getattr(self, "_n_deep", 0)
         if name == "ups":
             return self.flat_grad[:n_ups]
         if name == "rest":
             return self.flat_grad[n_ups:]
+        if name == "deep":
+            return self.flat_grad[n_ups:n_ups + n_deep]
+        if name == "tail":
+            return self.flat_grad[n_ups + n_deep:]
         raise KeyError(name)
 
     def grads_in_parameter_layout(self, params):
@@ -366,8 +370,17 @@ class GeneratorRuntime(_NetRuntimeBase):
         self.cpad = max(4, (in_channels + 3) // 4 * 4)
         convs = list(downs) + list(ups)
         bns = [b for b in down_bns if b is not None] + [b for b in up_bns if b is not None]
-        self._grad_order = list(ups) + list(downs)
-        self._n_ups = sum((16 * c.d0 * c.d1 + 3) // 4 * 4 for c in ups)
+        # flat gradient buffer = [up-conv weights | deep down-conv weights (levels >= DEEP_LEVEL, innermost first: the order in
+        # which the encoder half of the backward pass completes them) | the other down convs | biases, BatchNorm]: three
+        # buckets ("ups", "deep", "tail") that become final -- and can go on the wire / into Adam -- one after the other
+        self.deep_level = min(5, self.L)
+        deep = [downs[k - 1] for k in range(self.L, self.deep_level - 1, -1)]
+        shallow = [downs[k - 1] for k in range(self.deep_level - 1, 0, -1)]
+        self.deep_convs = deep
+        self._grad_order = list(ups) + deep + shallow
+        pad4 = lambda c: (16 * c.d0 * c.d1 + 3) // 4 * 4
+        self._n_ups = sum(pad4(c) for c in ups)
+        self._n_deep = sum(pad4(c) for c in deep)
         super().__init__(convs, bns, precision)
 
     def sizes(self, h, w):
@@ -499,12 +512,13 @@ class GeneratorRuntime(_NetRuntimeBase):
         self.ups[0].forward(x, 2 * h1, 2 * w1, out_nchw=out, act=ACT_TANH)
         return out
 
-    def backward(self, ws, dout, need_input_grad, param_grads=True, part=None):
+    def backward(self, ws, dout, need_input_grad, param_grads=True, part=None, on_deep=None):
         """dout: NCHW fp32 gradient of the output.  Accumulates parameter gradients into the flat buffer;
         returns the NHWC gradient of the packed input (or None).
         `part`: None = the whole pass; "dec" = the decoder half only (afterwards every up-conv weight gradient -- the
         "ups" gradient bucket, 64 % of the network's parameters -- is final, so its all-reduce can run under the encoder half);
-        "enc" = the rest (dout is ignored)."""
+        "enc" = the rest (dout is ignored).  `on_deep` (encoder half): called -- with the stream the weight-gradient kernels
+        run on as the current stream -- right after the last weight gradient of the "deep" bucket has been issued."""
         dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
         training = ws["training"]
         n = ws["n"]
@@ -512,7 +526,7 @@ class GeneratorRuntime(_NetRuntimeBase):
         new = lambda hh, ww, c: torch.empty((n, hh, ww, c), dtype=dt, device=dev)
         if part == "enc":
             dcat = ws.pop("_dcat_last")
-            return self._backward_encoder(ws, dcat, need_input_grad, param_grads)
+            return self._backward_encoder(ws, dcat, need_input_grad, param_grads, on_deep)
         ws["arena"].acc.zero_()            # all BatchNorm backward reductions of this pass accumulate into it
         # ---- outermost up conv (+Tanh)
         up = self.ups[0]
@@ -541,9 +555,9 @@ class GeneratorRuntime(_NetRuntimeBase):
             ws["_dcat_last"] = dcat
             self._join_side(ws)
             return None
-        return self._backward_encoder(ws, dcat, need_input_grad, param_grads)
+        return self._backward_encoder(ws, dcat, need_input_grad, param_grads, on_deep)
 
-    def _backward_encoder(self, ws, dcat, need_input_grad, param_grads):
+    def _backward_encoder(self, ws, dcat, need_input_grad, param_grads, on_deep=None):
         dt, dev, L, s = self.act_dtype, self.device(), self.L, ws["s"]
         training, n = ws["training"], ws["n"]
         C = [None] + [d.cout for d in self.downs]
@@ -568,6 +582,11 @@ class GeneratorRuntime(_NetRuntimeBase):
             if param_grads:
                 self._wgrad_async(ws, lambda down=down, x_in=x_in, gy=gy, thin_in=thin_in:
                                   down.wgrad(x_in, gy, x_bordered=ws["inp_b"] if thin_in else None), gy)
+            if on_deep is not None and k == self.deep_level:
+                import contextlib
+                with (torch.cuda.stream(self.side_stream) if (self.side_stream is not None and param_grads)
+                      else contextlib.nullcontext()):
+                    on_deep()
             if k > 1:
                 da = down.dgrad(gy, *s[k - 1])
             elif need_input_grad:

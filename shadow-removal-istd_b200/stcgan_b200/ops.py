@@ -267,6 +267,13 @@ def bn_act_bwd(y, scale_shift, mean_invstd, gamma, training, g1, act1, g2, act2,
     _, _, _, _, lddy = _nhwc(dy)
     lib = _lib.load()
     p = lambda t: None if t is None else t.data_ptr()
+    if (scale_shift is not None and training and dbias is None and y.dtype == torch.bfloat16
+            and n * h * w * c <= SMALL_BN_ELEMS and _SMALL_BN):
+        # bottleneck-sized tensor: reduce + apply in ONE single-block launch (stcgan_bn_act_bwd_small)
+        check(lib.stcgan_bn_act_bwd_small(_code(y), y.data_ptr(), n, h, w, c, ldy, scale_shift.data_ptr(), mean_invstd.data_ptr(),
+                                          gamma.data_ptr(), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2, dy.data_ptr(),
+                                          lddy, p(dgamma), p(dbeta), _stream()), "stcgan_bn_act_bwd_small")
+        return
     if scale_shift is not None and training:
         check(lib.stcgan_bn_act_bwd_reduce(_code(y), y.data_ptr(), n, h, w, c, ldy, scale_shift.data_ptr(),
                                            mean_invstd.data_ptr(), hc, wc, g1.data_ptr(), ldg1, act1, p(g2), ldg2, act2,
@@ -409,6 +416,9 @@ def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None, border=0):
                                          g.data_ptr(), ld, _stream()), "stcgan_out_act_bwd")
     return g
 
+
+SMALL_BN_ELEMS = 256 * 512
+_SMALL_BN = _os.environ.get("STCGAN_SMALL_BN", "1") != "0"
 
 KIND_L1, KIND_MSE, KIND_BCE = 0, 1, 2
 

@@ -86,7 +86,7 @@ def _worker(rank, world, port, mode, out_dir):
             *(t.double() for t in shards[0]), keep_grads=True)
         far = rel_err(torch.cat([t.reshape(-1) for t in grads(eng, nets, "D1")]),
                       torch.cat([t.reshape(-1) for t in solo["grads_D"]["D1"]]))
-        assert far > 10 * max(worst, 1e-3), (far, worst)
+        assert far > (10 if tight else 1.5) * max(worst, 1e-3), (far, worst)
         # update direction of every network vs the data-parallel oracle's single Adam step
         for n in nets:
             agree = total = 0
