@@ -217,7 +217,7 @@ int stcgan_bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, 
                           float* running_mean, float* running_var, float momentum, float eps, int training,
                           float* mean_invstd, float* scale_shift, int HC, int WC,
                           void* out1, int ld1, int act1, void* out2, int ld2, int act2, void* stream);
-/* training-mode BatchNorm(+activation) backward of a SMALL tensor (N*H*W*C <= 256*512 elements, bf16: the U-Net bottleneck
+/* training-mode BatchNorm(+activation) backward of a SMALL tensor (N*H*W*C <= 64*512 elements, bf16: the innermost U-Net
  * levels) as ONE single-block launch: reduce, coefficients and apply of the two functions below in one kernel, same
  * arithmetic.  Returns STCGAN_EUNSUPPORTED for larger tensors / other dtypes (run the two-pass form then).  dgamma / dbeta
  * are ACCUMULATED into (NULL = skip). */

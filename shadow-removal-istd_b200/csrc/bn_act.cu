@@ -542,10 +542,11 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// small tensors (the U-Net bottleneck: <= 256 pixels x 512 channels): reduce + apply in ONE single-block launch.  The two-pass
-// form costs two dependent ~7 us launches on tensors of a few hundred KB -- pure latency on the backward pass's critical
-// chain (16 such BatchNorm layers per train step); one 1024-thread block reduces in shared memory, derives the coefficients
-// and applies them (the second read of y / g hits L1/L2).  Same arithmetic as the two-pass kernels: fp32 partial sums per
+// tiny tensors (the innermost U-Net levels: <= 64 pixels x 512 channels): reduce + apply in ONE single-block launch.  The
+// two-pass form costs two dependent ~7 us launches -- pure latency on the backward pass's critical chain; one 1024-thread
+// block reduces in shared memory, derives the coefficients and applies them (the second read of y / g hits L1/L2).  One SM
+// streams ~100 GB/s, so this only wins below ~0.5 MB of traffic: measured on B200, 256-pixel tensors (1.8 MB) took 30 us
+// this way against 14 us in two passes, hence the 64-pixel bound.  Same arithmetic as the two-pass kernels: fp32 partial sums per
 // thread, fp64 across the block.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -649,14 +650,8 @@ static inline unsigned stream_grid(long long P, int rows, K kernel, size_t smem,
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// STCGAN_BN_VAR (tuning experiments, bf16 kernels): 0 = 4 pixels in flight per thread, 2 blocks/SM (round-1 shape);
-// 1 = 2 in flight, 4 blocks/SM; 2 = 4 in flight, 3 blocks/SM; 3 = 2 in flight, 3 blocks/SM
-static int bn_variant() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("STCGAN_BN_VAR"); v = e ? atoi(e) : 0; if (v < 0 || v > 3) v = 0; }
-  return v;
-}
-
+// (Measured on B200, round 2: 4 pixels in flight per thread at 1-2 blocks/SM -- the shapes below -- beat 2 in flight at 3-4
+// blocks/SM and 4 in flight at 3 blocks/SM by 5-20 % of the whole train step: the register-starved variants spill.)
 template <typename T>
 static int bn_stats_t(const void* y, long long P, int C, int ld, double* acc, int want_sq, cudaStream_t st) {
   const RowMap m = row_map(C);
@@ -722,18 +717,10 @@ int bn_fused_apply(int dtype, const void* y, int N, int H, int W, int C, int ldy
     launch_k(bn_fused_apply_kernel<float>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<float>, smem), 256, smem, st,
              static_cast<const float*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<float*>(o1), ld1, act1,
              static_cast<float*>(o2), ld2, act2, m.cv, m.rows);
-  else {
-#define FA_LAUNCH(U_, MB_) launch_k(bn_fused_apply_kernel<__nv_bfloat16, U_, MB_>, stream_grid(PC, m.rows * U_, bn_fused_apply_kernel<__nv_bfloat16, U_, MB_>, smem), 256, smem, st, \
-             static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1, \
-             static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows)
-    switch (bn_variant()) {
-      case 1: FA_LAUNCH(2, 4); break;
-      case 2: FA_LAUNCH(4, 3); break;
-      case 3: FA_LAUNCH(2, 3); break;
-      default: FA_LAUNCH(4, 1); break;
-    }
-#undef FA_LAUNCH
-  }
+  else
+    launch_k(bn_fused_apply_kernel<__nv_bfloat16>, stream_grid(PC, m.rows * 4, bn_fused_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
+             static_cast<const __nv_bfloat16*>(y), H, W, C, ldy, f, HC, WC, PC, static_cast<__nv_bfloat16*>(o1), ld1, act1,
+             static_cast<__nv_bfloat16*>(o2), ld2, act2, m.cv, m.rows);
   return finish_launch();
 }
 
@@ -749,18 +736,9 @@ int bn_act_bwd_reduce(int dtype, const void* y, int N, int H, int W, int C, int 
   if (dtype == STCGAN_F32)
     launch_k(bn_bwd_reduce_kernel<float>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<float>, smem, 4), 256, smem, st, static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const float*>(g1), ldg1, act1,
         static_cast<const float*>(g2), ldg2, act2, acc, m.cv, m.rows);
-  else {
-#define BR_LAUNCH(U_, MB_) launch_k(bn_bwd_reduce_kernel<__nv_bfloat16, U_, MB_>, stream_grid(P, m.rows * U_, bn_bwd_reduce_kernel<__nv_bfloat16, U_, MB_>, smem, 4), 256, smem, st, \
-        static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1, \
-        act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows)
-    switch (bn_variant()) {
-      case 1: BR_LAUNCH(2, 4); break;
-      case 2: BR_LAUNCH(4, 3); break;
-      case 3: BR_LAUNCH(2, 3); break;
-      default: BR_LAUNCH(4, 2); break;
-    }
-#undef BR_LAUNCH
-  }
+  else
+    launch_k(bn_bwd_reduce_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_reduce_kernel<__nv_bfloat16>, smem, 4), 256, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1,
+        act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, m.cv, m.rows);
   return finish_launch();
 }
 
@@ -781,19 +759,11 @@ int bn_act_bwd_apply(int dtype, const void* y, int N, int H, int W, int C, int l
              static_cast<const float*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, static_cast<const float*>(g1), ldg1,
              act1, static_cast<const float*>(g2), ldg2, act2, acc, static_cast<float*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows,
              1.0 / (double)P);
-  else {
-#define BA_LAUNCH(U_, MB_) launch_k(bn_bwd_apply_kernel<__nv_bfloat16, U_, MB_>, stream_grid(P, m.rows * U_, bn_bwd_apply_kernel<__nv_bfloat16, U_, MB_>, smem), 256, smem, st, \
-             static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC, \
-             static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc, \
-             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows, 1.0 / (double)P)
-    switch (bn_variant()) {
-      case 1: BA_LAUNCH(2, 4); break;
-      case 2: BA_LAUNCH(4, 3); break;
-      case 3: BA_LAUNCH(2, 3); break;
-      default: BA_LAUNCH(4, 2); break;
-    }
-#undef BA_LAUNCH
-  }
+  else
+    launch_k(bn_bwd_apply_kernel<__nv_bfloat16>, stream_grid(P, m.rows * 4, bn_bwd_apply_kernel<__nv_bfloat16>, smem), 256, smem, st,
+             static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi, gamma, training, HC, WC,
+             static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2, acc,
+             static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, dbias, m.cv, m.rows, 1.0 / (double)P);
   return finish_launch();
 }
 
@@ -803,7 +773,7 @@ int bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int l
                      const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
                      int act2, void* dy, int lddy, float* dgamma, float* dbeta, cudaStream_t st) {
   const long long P = (long long)N * H * W;
-  if (dtype != STCGAN_BF16 || C % VEC != 0 || C > 1024 || P * C > 256LL * 512 || P < 1) return STCGAN_EUNSUPPORTED;
+  if (dtype != STCGAN_BF16 || C % VEC != 0 || C > 1024 || P * C > 64LL * 512 || P < 1) return STCGAN_EUNSUPPORTED;
   if (!ss || !mi || !gamma || !g1 || !dy || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2) ||
       !vec_ok(dtype, dy, lddy))
     return STCGAN_EINVAL;

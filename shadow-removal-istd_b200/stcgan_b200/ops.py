@@ -417,7 +417,7 @@ def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None, border=0):
     return g
 
 
-SMALL_BN_ELEMS = 256 * 512
+SMALL_BN_ELEMS = 64 * 512
 _SMALL_BN = _os.environ.get("STCGAN_SMALL_BN", "1") != "0"
 
 KIND_L1, KIND_MSE, KIND_BCE = 0, 1, 2

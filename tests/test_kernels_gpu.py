@@ -228,7 +228,7 @@ def test_pack_weight_layout(cuda, lib):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("shape", [(2, 9, 7, 64), (16, 4, 4, 512), (1, 2, 2, 8), (3, 31, 31, 128)])
+@pytest.mark.parametrize("shape", [(2, 9, 7, 64), (16, 4, 4, 512), (16, 2, 2, 512), (1, 2, 2, 8), (3, 31, 31, 128)])
 @pytest.mark.parametrize("training", [True, False])
 def test_batchnorm_act_forward_backward(cuda, lib, mode, shape, training):
     """BN(train/eval) + LeakyReLU and ReLU dual output, with a crop, against torch ops in float64."""
