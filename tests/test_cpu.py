@@ -195,3 +195,32 @@ def test_install_into_reference_shim():
             "assert type(g) is S.UnetGenerator and type(d) is S.NLayerDiscriminator; print('ok')")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_data_parallel_oracle_and_precision_emulation_are_consistent():
+    """Round-2 additions to the oracle (test infrastructure of the multi-rank and bf16-bound GPU tests): the single-process
+    data-parallel statement with ONE shard is the plain train step, bit for bit; with two shards its gradients are the mean of
+    the per-shard gradients (nn.DataParallel semantics, src/cgan.py:78-84); the bf16 emulation only rounds convolution
+    operands (it is the identity on values that are already bf16-representable zero tensors, and a small perturbation else)."""
+    torch.manual_seed(1)
+    st = O.build_all_states(ngf=8, ndf=8)
+    sh = [tuple(t.double() for t in O.make_istd_batch(1, 256, 256, seed=3 + i)) for i in range(2)]
+    a = O.OracleTrainer(st, dtype=torch.float64)
+    ra = a.train_step(*sh[0], keep_grads=True)
+    b = O.OracleDataParallel(st, 1, dtype=torch.float64)
+    rb, gb = b.train_step([sh[0]])
+    assert float(ra["G_loss"]) == float(rb[0]["G_loss"]) and float(ra["D_loss"]) == 0.5 * float(rb[0]["D1_loss"]) + 0.5 * float(rb[0]["D2_loss"])
+    for n in a.params:
+        for p, q in zip(a.params[n], b.t.params[n]):
+            assert torch.equal(p, q)
+    # two shards: D-phase gradients == mean of the two single-shard gradient sets
+    solo = [O.OracleTrainer(st, dtype=torch.float64).train_step(*s, do_optim=False, keep_grads=True)["grads_D"] for s in sh]
+    _, g2 = O.OracleDataParallel(st, 2, dtype=torch.float64).train_step(sh)
+    for n in ("D1", "D2"):
+        for ga, gb_, gm in zip(solo[0][n], solo[1][n], g2[n]):
+            assert torch.allclose((ga + gb_) / 2, gm, rtol=1e-10, atol=1e-14)
+    # bf16 emulation: perturbs the step at the bf16 rounding level, nothing more
+    with O.emulate_conv_precision(torch.bfloat16):
+        re_ = O.OracleTrainer(st, dtype=torch.float64).train_step(*sh[0])
+    e = rel_err(re_["y_pred"], ra["y_pred"])
+    assert 1e-5 < e < 5e-2, e
