@@ -221,8 +221,12 @@ class STCGANEngine:
         # schedule switches (experiments / A-B measurements; the defaults are the measured-best combination)
         flag = lambda name, default: os.environ.get(name, default) != "0"
         self._early_d1 = conc and flag("STCGAN_EARLY_D1", "1")        # D1's exchange + Adam share + G-phase passes under G2's forward
-        self._adam_early = conc and flag("STCGAN_ADAM_EARLY", "1")    # G2's / G1.ups' Adam shares under the halves of G1's backward
+        # G2's / G1.ups' / G1.deep's Adam shares underneath the halves of G1's backward: +0.5 % on one GPU, but at N > 1 the
+        # HBM-bound Adam kernels slow the NCCL kernels that share G1's backward with them, the serial chain of all-reduces
+        # slips and the last bucket lands late (measured at 8 GPUs: 7.42 ms per step with it, 6.98 ms without) -> single GPU only
+        self._adam_early = conc and flag("STCGAN_ADAM_EARLY", "1" if self.world == 1 else "0")
         self._overlap_real = conc and flag("STCGAN_OVERLAP_REAL", "1")  # D2's G-phase real pass next to its fake pass
+        self._deep_bucket = flag("STCGAN_DEEP_BUCKET", "1")           # N > 1: G1's deep encoder gradients go on the wire early
         self._graph = None
         self._graphs = []
         self._static = None
@@ -475,8 +479,9 @@ class STCGANEngine:
             deep["ev"] = torch.cuda.Event()
             deep["ev"].record()
 
+        deep_early = early or (multi and split and self._deep_bucket)
         with self._critical():
-            rt["G1"].backward(wg1, dm, False, part="enc", on_deep=deep_done if early else None)
+            rt["G1"].backward(wg1, dm, False, part="enc", on_deep=deep_done if deep_early else None)
         if early:
             with L.lane(0):
                 if deep["ev"] is not None:
@@ -490,6 +495,11 @@ class STCGANEngine:
                 if multi:
                     yield ("G1.tail",), True
                 self.optim_G.step_partial(self._g1_tail, tick=False, last=True)
+            elif deep_early:                                  # (N > 1) only the small tail bucket is still to be exchanged
+                yield ("G1.tail",), False, ("G1.ups",)
+                self.optim_G.step_partial(self._g1_ups, tick=False, last=False)   # under the tail's all-reduce
+                yield (), True
+                self.optim_G.step_partial(self._g1_rest, tick=False, last=True)
             else:
                 if multi:
                     yield ("G1.rest",), False, ("G1.ups",)
