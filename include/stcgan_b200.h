@@ -171,6 +171,12 @@ int stcgan_thinwgrad(const void* t, int N, int HP, int WP, int stride, int thin_
  * y_nhwc8: bf16 [N, OH, OW, >= 8] pitch ldy, channels cout..7 written as zeros.  Exactly one of the two is non-NULL. */
 int stcgan_thin_col2im(int mode, const void* x, int N, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
                        const float* bias, int act, float* y_nchw_f32, void* y_nhwc8, int ldy, int OH, int OW, void* stream);
+/* The generators' last layer for CGAN.infer (src/cgan.py:437-446): ConvTranspose2d(128 -> cout <= 8, k4 s2 p1) + bias + Tanh as
+ * above (mode 0), with the image quantisation of utils.float2uint (src/utils.py:65-67) INSIDE the same epilogue:
+ * y_nhwc_u8[n,oy,ox,c] = (uint8) trunc(clip(act(v) * 0.5 + 0.5, 0, 1) * 255), float32 arithmetic like numpy (bit-exact with
+ * quantising the float output afterwards).  y_nchw_f32 may be NULL when only the image is wanted. */
+int stcgan_thin_convt_u8(const void* x, int N, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
+                         const float* bias, int act, float* y_nchw_f32, uint8_t* y_nhwc_u8, int OH, int OW, void* stream);
 /* wt[(t*cpad + r)][k] = W(r, k, t) with (r, k) = (d0, d1) if n_is_d0 else (d1, d0), zero rows for r >= the thin dimension */
 int stcgan_pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, void* stream);
 /* thin weight packings from the torch parameter W[d0][d1][4][4] (fp32) to bf16 */

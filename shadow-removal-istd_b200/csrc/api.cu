@@ -28,7 +28,7 @@ int tapwgrad_tc(int geom, const void* S, int N, int SH, int SW, int D0, int lds,
                 const void* L, int LH, int LW, int D1, int ldl, float* G, cudaStream_t st);
 // thin_col2im.cu
 int thin_col2im_tc(int mode, const void* x, int NB, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
-                   const float* bias, int act, float* y32, void* y8, int ldy, int OH, int OW, cudaStream_t st);
+                   const float* bias, int act, float* y32, void* y8, int ldy, int OH, int OW, cudaStream_t st, uint8_t* u8);
 int pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, cudaStream_t st);
 // bn_act.cu
 int bn_stats(int dtype, const void* y, long long P, int C, int ld, double* acc, cudaStream_t st);
@@ -283,7 +283,17 @@ int stcgan_thin_col2im(int mode, const void* x, int N, int IH, int IW, int K, in
   STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_SIGMOID);
   STCGAN_REQUIRE(mode == 0 ? (OH <= 2 * IH + 1 && OW <= 2 * IW + 1) : (mode == 1 && OH == IH - 1 && OW == IW - 1));
   if (N == 0) return 0;
-  return thin_col2im_tc(mode, x, N, IH, IW, K, ldx, wt, cpad, cout, bias, act, y_nchw_f32, y_nhwc8, ldy, OH, OW, as_stream(stream));
+  return thin_col2im_tc(mode, x, N, IH, IW, K, ldx, wt, cpad, cout, bias, act, y_nchw_f32, y_nhwc8, ldy, OH, OW, as_stream(stream),
+                        nullptr);
+}
+
+int stcgan_thin_convt_u8(const void* x, int N, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
+                         const float* bias, int act, float* y_nchw_f32, uint8_t* y_nhwc_u8, int OH, int OW, void* stream) {
+  STCGAN_REQUIRE(x && wt && y_nhwc_u8 && N >= 0 && IH > 0 && IW > 0 && K > 0 && ldx >= K && OH > 0 && OW > 0);
+  STCGAN_REQUIRE(act >= STCGAN_ACT_NONE && act <= STCGAN_ACT_SIGMOID && OH <= 2 * IH + 1 && OW <= 2 * IW + 1);
+  if (N == 0) return 0;
+  return thin_col2im_tc(0, x, N, IH, IW, K, ldx, wt, cpad, cout, bias, act, y_nchw_f32, nullptr, 0, OH, OW, as_stream(stream),
+                        y_nhwc_u8);
 }
 
 int stcgan_pack_weight_tapn(const float* w, int D0, int D1, int n_is_d0, int cpad, void* out, void* stream) {

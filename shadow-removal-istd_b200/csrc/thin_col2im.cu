@@ -34,7 +34,16 @@ struct alignas(64) PixGemmParams {
   float* y32;              // NCHW fp32 [NB, cout, OH, OW] (bias + activation), or
   __nv_bfloat16* y8;       // NHWC bf16, 8 channels per pixel (channels >= cout are written as zeros), pitch ldy
   int ldy;
+  uint8_t* u8;             // optional, next to (or instead of) y32 in mode 0: NHWC uint8 [NB, OH, OW, cout] =
+                           // utils.float2uint(act(v) * 0.5 + 0.5), the image CGAN.infer writes (src/cgan.py:441-446)
 };
+
+// (np.clip(a * 0.5 + 0.5, 0, 1) * 255).astype(uint8) in float32 like numpy: two roundings (no FMA), truncation
+__device__ __forceinline__ uint8_t quantise_u8(float a) {
+  float t = __fadd_rn(__fmul_rn(a, 0.5f), 0.5f);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  return (uint8_t)(__fmul_rn(t, 255.f));
+}
 
 template <int NN, int STAGES>
 struct PixSmem {
@@ -140,7 +149,7 @@ pixgemm_col2im_kernel(const __grid_constant__ PixGemmParams P) {
     const int tw = P.tw, cpad = P.cpad;
     if (P.mode == 0) {
       const int OHt = 2 * P.th - 2, OWt = 2 * tw - 2, oy_base = 2 * r0 + 1, ox_base = 2 * c0 + 1;
-      if (P.y32) {
+      if (P.y32 || P.u8) {
         const int total = P.cout * OHt * OWt;
         for (int idx = et; idx < total; idx += 128) {
           const int lx = idx % OWt, ly = (idx / OWt) % OHt, co = idx / (OWt * OHt);
@@ -152,7 +161,9 @@ pixgemm_col2im_kernel(const __grid_constant__ PixGemmParams P) {
           float v = p00[(khA * 4 + kwA) * cpad] + p00[SM::P_PITCH + (khA * 4 + kwB) * cpad] +
                     p10[(khB * 4 + kwA) * cpad] + p10[SM::P_PITCH + (khB * 4 + kwB) * cpad];
           if (P.bias) v += __ldg(P.bias + co);
-          P.y32[(((long long)n * P.cout + co) * P.OH + oy) * P.OW + ox] = thin_act(P.act, v);
+          const float a = thin_act(P.act, v);
+          if (P.y32) P.y32[(((long long)n * P.cout + co) * P.OH + oy) * P.OW + ox] = a;
+          if (P.u8) P.u8[(((long long)n * P.OH + oy) * P.OW + ox) * P.cout + co] = quantise_u8(a);
         }
       } else {
         const int total = OHt * OWt;
@@ -221,10 +232,10 @@ static int launch_pixgemm(const PixGemmParams& P, unsigned grid, cudaStream_t st
 // mode 0: stride-2 scatter (OH <= 2*IH + 1, OW <= 2*IW + 1), mode 1: stride-1 gather (OH <= IH - 1, OW <= IW - 1)
 // wt: packed weights [(tap * cpad + c)][K] bf16 (stcgan_pack_weight_tapn), cpad in {1, 4, 8}, cout <= cpad
 int thin_col2im_tc(int mode, const void* x, int NB, int IH, int IW, int K, int ldx, const void* wt, int cpad, int cout,
-                   const float* bias, int act, float* y32, void* y8, int ldy, int OH, int OW, cudaStream_t st) {
+                   const float* bias, int act, float* y32, void* y8, int ldy, int OH, int OW, cudaStream_t st, uint8_t* u8) {
   if (K % 64 != 0 || ldx % 8 != 0 || !al16(x) || !al16(wt)) return STCGAN_EUNSUPPORTED;
   if ((cpad != 1 && cpad != 4 && cpad != 8) || cout < 1 || cout > cpad) return STCGAN_EINVAL;
-  if ((y32 == nullptr) == (y8 == nullptr)) return STCGAN_EINVAL;
+  if (u8 ? (mode != 0 || y8 != nullptr) : ((y32 == nullptr) == (y8 == nullptr))) return STCGAN_EINVAL;
   if (y8 && (mode != 0 || bias || act != STCGAN_ACT_NONE || ldy % 8 != 0 || ldy < 8 || !al16(y8))) return STCGAN_EUNSUPPORTED;
   if (mode != 0 && mode != 1) return STCGAN_EINVAL;
   PixGemmParams P;
@@ -240,7 +251,7 @@ int thin_col2im_tc(int mode, const void* x, int NB, int IH, int IW, int K, int l
     if (best < 0 || tiles < best || (tiles == best && tw > P.tw)) { best = tiles; P.tw = tw; P.th = th; P.tiles_w = (int)tw_n; P.tiles_h = (int)th_n; }
   }
   P.kchunks = K / 64; P.mode = mode; P.OH = OH; P.OW = OW; P.NB = NB; P.cpad = cpad; P.cout = cout; P.act = act;
-  P.bias = bias; P.y32 = y32; P.y8 = static_cast<__nv_bfloat16*>(y8); P.ldy = ldy;
+  P.bias = bias; P.y32 = y32; P.y8 = static_cast<__nv_bfloat16*>(y8); P.ldy = ldy; P.u8 = u8;
   int rc = encode_nhwc(&P.amap, x, K, IW, IH, NB, ldx, (long long)IW * ldx, (long long)IH * IW * ldx, P.tw, P.th, 1);
   if (rc) return rc;
   const int NN = 16 * cpad;

@@ -74,6 +74,7 @@ SIGNATURES = {
     "stcgan_thinconv": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
     "stcgan_thinwgrad": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "stcgan_thin_col2im": (_i, [_i, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _p]),
+    "stcgan_thin_convt_u8": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _i, _p, _p, _i, _i, _p]),
     "stcgan_pack_weight_tapn": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight_thin": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "stcgan_pack_weight_pad16": (_i, [_p, _i, _i, _i, _p, _p]),

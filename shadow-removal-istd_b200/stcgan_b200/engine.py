@@ -696,14 +696,20 @@ class STCGANEngine:
 
 
 @torch.no_grad()
-def infer(G1, G2, x, quantize=True):
+def infer(G1, G2, x, quantize=True, want_float=True):
     """CGAN.infer core (src/cgan.py:437-446 + utils.float2uint): eval-mode G1 -> G2; returns
-    (m_pred, y_pred [NCHW fp32], m_u8, y_u8 [N,H,W,C] uint8 or None)."""
+    (m_pred, y_pred [NCHW fp32], m_u8, y_u8 [N,H,W,C] uint8 or None).  On the bf16 path the uint8 images come out of the
+    last layers' epilogues; `want_float=False` (uint8-only callers) then skips y_pred's float output (y_pred is None;
+    m_pred is always produced, it is G2's input)."""
     if G1.training or G2.training:
         raise RuntimeError("infer() expects G1.eval(); G2.eval() like the reference (cgan.py:422-423)")
     rt1, rt2 = G1.runtime(), G2.runtime()
     x = x.contiguous()
     if os.environ.get("STCGAN_INFER_FOLD", "1") != "0":
+        if quantize:                                # ... and the uint8 quantisation into the last layers' epilogues
+            mp, m8 = rt1.forward_inference([x], quantize=True)
+            yp, y8 = rt2.forward_inference([x, mp], quantize=True, want_float=want_float)
+            return mp, yp, m8, y8
         mp = rt1.forward_inference([x])             # BatchNorm(eval) + activations folded into the conv epilogues
         yp = rt2.forward_inference([x, mp])
     else:
@@ -723,7 +729,7 @@ def infer_u8(G1, G2, x_u8, out_m=None, out_y=None):
     dev = next(G1.parameters()).device
     x8 = x_u8 if x_u8.is_cuda else x_u8.to(dev, non_blocking=True)
     x = ops.u8_to_nchw(x8)
-    _, _, m8, y8 = infer(G1, G2, x)
+    _, _, m8, y8 = infer(G1, G2, x, want_float=False)
     if out_m is not None:
         out_m.copy_(m8, non_blocking=True)
     if out_y is not None:
@@ -771,7 +777,7 @@ class InferencePipeline:
         main.wait_event(sl["ready"])
         x = ops.u8_to_nchw(sl["x8"])
         sl["consumed"].record(main)
-        _, _, m8, y8 = infer(self.G1, self.G2, x)
+        _, _, m8, y8 = infer(self.G1, self.G2, x, want_float=False)
         sl["computed"].record(main)
         self.cout.wait_event(sl["computed"])
         with torch.cuda.stream(self.cout):

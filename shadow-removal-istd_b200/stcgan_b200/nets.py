@@ -454,8 +454,10 @@ class GeneratorRuntime(_NetRuntimeBase):
         ws["out"] = out
         return out, ws
 
-    def forward_inference(self, sources, packed=None):
-        """Eval-mode forward that keeps nothing for a backward pass (CGAN.infer, src/cgan.py:422-438).  On the bf16 tensor-core
+    def forward_inference(self, sources, packed=None, quantize=False, want_float=True):
+        """Eval-mode forward that keeps nothing for a backward pass (CGAN.infer, src/cgan.py:422-438).  `quantize`: the last
+        layer's epilogue also writes the uint8 HWC image of utils.float2uint (cgan.py:441-446) and (out, u8) is returned;
+        `want_float=False` then skips the float output altogether (out is None).  On the bf16 tensor-core
         path every BatchNorm(eval) + LeakyReLU / ReLU is folded into the producing convolution's epilogue (per-channel scale /
         shift from the running statistics, stcgan_tapconv_ep), the encoder writes both activations of a level -- LeakyReLU for
         the next down conv, ReLU into the left half of the decoder's concat buffer -- from one accumulator, and the decoder's
@@ -468,7 +470,8 @@ class GeneratorRuntime(_NetRuntimeBase):
                            for c in list(self.downs[1:]) + list(self.ups[1:])))
         inp, inp_b = self._packed_input(sources, packed)
         if not fold_ok or inp_b is None:
-            return self.forward(sources, False, packed=packed)[0]
+            out = self.forward(sources, False, packed=packed)[0]
+            return (out, ops.float2uint_hwc(out)) if quantize else out
         dt, dev = self.act_dtype, self.device()
         n, _, h, w = sources[0].shape
         s = self.sizes(h, w)
@@ -508,8 +511,13 @@ class GeneratorRuntime(_NetRuntimeBase):
                            out=dst[..., C[k - 1]:], crop=(dst.shape[1], dst.shape[2]))
             x = dst
         h1, w1 = s[1]
-        out = torch.empty((n, self.cout, 2 * h1, 2 * w1), dtype=torch.float32, device=dev)
-        self.ups[0].forward(x, 2 * h1, 2 * w1, out_nchw=out, act=ACT_TANH)
+        up = self.ups[0]
+        out = torch.empty((n, self.cout, 2 * h1, 2 * w1), dtype=torch.float32, device=dev) if (want_float or not quantize) else None
+        if quantize:
+            u8 = ops.thin_convT_u8(x, up.wtn, up.cpad, up.cout, 2 * h1, 2 * w1, bias=None if up.bias is None else up.bias.detach(),
+                                   act=ACT_TANH, out_nchw=out)
+            return out, u8
+        up.forward(x, 2 * h1, 2 * w1, out_nchw=out, act=ACT_TANH)
         return out
 
     def backward(self, ws, dout, need_input_grad, param_grads=True, part=None, on_deep=None):

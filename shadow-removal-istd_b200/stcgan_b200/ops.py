@@ -343,6 +343,22 @@ def thin_col2im(mode, x, wt, cpad, cout, oh, ow, *, bias=None, act=ACT_NONE, out
           "stcgan_thin_col2im")
 
 
+def thin_convT_u8(x, wt, cpad, cout, oh, ow, *, bias=None, act=ACT_TANH, out_nchw=None):
+    """the generators' last layer with the uint8 image quantisation in its epilogue (see stcgan_thin_convt_u8): returns the
+    uint8 [N, OH, OW, cout] image; `out_nchw` (fp32 [N, cout, OH, OW]) additionally receives the float output."""
+    _need_cuda(x, wt)
+    n, ih, iw, k, ldx = _nhwc(x)
+    assert x.dtype == torch.bfloat16 and wt.dtype == torch.bfloat16 and wt.numel() == 16 * cpad * k
+    if out_nchw is not None:
+        assert out_nchw.dtype == torch.float32 and out_nchw.is_contiguous() and tuple(out_nchw.shape) == (n, cout, oh, ow)
+    u8 = torch.empty((n, oh, ow, cout), dtype=torch.uint8, device=x.device)
+    check(_lib.load().stcgan_thin_convt_u8(x.data_ptr(), n, ih, iw, k, ldx, wt.data_ptr(), cpad, cout,
+                                           None if bias is None else bias.data_ptr(), act,
+                                           None if out_nchw is None else out_nchw.data_ptr(), u8.data_ptr(), oh, ow, _stream()),
+          "stcgan_thin_convt_u8")
+    return u8
+
+
 def pack_weight_tapn(w, n_is_d0, cpad, out):
     d0, d1 = w.shape[0], w.shape[1]
     check(_lib.load().stcgan_pack_weight_tapn(w.data_ptr(), d0, d1, int(n_is_d0), cpad, out.data_ptr(), _stream()),

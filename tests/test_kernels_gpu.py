@@ -562,3 +562,27 @@ def test_gpu_augmentation_matches_reference_golden(cuda, lib, case, kw):
         assert got.shape == want.shape
         assert np.array_equal(mine, want)       # the CPU restatement is pinned to the reference + OpenCV
         assert np.array_equal(got, want), float(np.abs(got - want).max())      # and the kernel reproduces it bit for bit
+
+
+@pytest.mark.parametrize("cout,n,h,w_", [(1, 2, 16, 20), (3, 3, 15, 9)])
+def test_last_layer_epilogue_quantises_to_uint8(cuda, lib, cout, n, h, w_):
+    """stcgan_thin_convt_u8: ConvTranspose2d(128 -> 1|3) + bias + Tanh with utils.float2uint (src/utils.py:65-67, as applied by
+    CGAN.infer, src/cgan.py:441-446) inside the epilogue == quantising the same launch's float output with numpy, bit for bit
+    -- with and without the float output."""
+    import stcgan_oracle as O
+    from stcgan_b200 import ops
+    from stcgan_b200._lib import ACT_TANH
+    op, w, b = _convop("convT", 128, cout, "bf16", cuda, bias=True)
+    assert op.thin == "coutT"
+    g = torch.Generator().manual_seed(2)
+    x = _nhwc(_round(torch.randn(n, 128, h, w_, generator=g) * 0.5, "bf16"), torch.bfloat16, cuda)
+    out = torch.empty((n, cout, 2 * h, 2 * w_), dtype=torch.float32, device=cuda)
+    u8 = ops.thin_convT_u8(x, op.wtn, op.cpad, cout, 2 * h, 2 * w_, bias=op.bias.detach(), act=ACT_TANH, out_nchw=out)
+    u8_only = ops.thin_convT_u8(x, op.wtn, op.cpad, cout, 2 * h, 2 * w_, bias=op.bias.detach(), act=ACT_TANH)
+    plain = torch.empty_like(out)
+    op.forward(x, 2 * h, 2 * w_, out_nchw=plain, act=ACT_TANH)
+    torch.cuda.synchronize()
+    assert torch.equal(out, plain)
+    want = O.float2uint(out.cpu().numpy().transpose(0, 2, 3, 1) * 0.5 + 0.5)
+    assert np.array_equal(u8.cpu().numpy(), want) and np.array_equal(u8_only.cpu().numpy(), want)
+    assert 0 < int(u8.max()) and int(u8.min()) < 255 and u8.float().std() > 1          # (a non-degenerate image)
