@@ -445,7 +445,10 @@ def run_b200(args, rank, world, local_rank):
             eng.release_graphs()
             del eng, nets
             torch.cuda.empty_cache()
-            cudnn = cudnn_baseline(dev, BATCH_PER_GPU, H, W)
+            try:
+                cudnn = cudnn_baseline(dev, BATCH_PER_GPU, H, W)
+            except Exception as e:      # a reported baseline must never cost the measured line
+                cudnn = {"error": f"{type(e).__name__}: {e}"[:300]}
     cfg = train_config(args.workload, world)
     cfg.update({"precision": "bf16 activations/weights, fp32 master weights + Adam + accumulation",
                 "l2": "per-step working set (>2 GB of activations and weights) exceeds the 126 MB L2; no explicit flush",
