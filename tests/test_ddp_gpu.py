@@ -98,9 +98,17 @@ def _worker(rank, world, port, mode, out_dir):
     eng.release_graphs()
     del eng, nets
     # ---- captured step: one eager warm-up + 2 replays == three eager steps ------------------------------------------------
-    nets_a, a = build()
-    for _ in range(3):
-        a.train_step(x, m, y)
+    # yardstick as in test_cuda_graph_replay_equals_eager: two IDENTICAL eager runs (a, c) drift apart through the order of the
+    # atomics and Adam's sign-like first steps; the captured run (b) must sit within a small multiple of that drift
+    def eager3():
+        nets_, e_ = build()
+        for _ in range(3):
+            e_.train_step(x, m, y)
+        torch.cuda.synchronize()
+        return flat_params(nets_), e_.losses.cpu().clone(), e_
+
+    pa, la, a = eager3()
+    pc, lc, c = eager3()
     nets_b, b = build()
     b.capture(x, m, y, warmup=1)
     assert len(b._graphs) == 1 and b._graph == "graph"
@@ -110,12 +118,18 @@ def _worker(rank, world, port, mode, out_dir):
     pb = flat_params(nets_b)
     ref0 = pb.clone(); dist.broadcast(ref0, 0)
     assert torch.equal(pb, ref0), "replicas diverged after graph replays"
-    la, lb = a.losses.cpu(), b.losses.cpu()
-    # (bf16: two runs of the same three steps drift apart through order-dependent rounding amplified by Adam -- see
-    # test_cuda_graph_replay_equals_eager -- so only the fp32 mode is compared tightly)
-    assert (la[:6] - lb[:6]).abs().max().item() <= (2e-3 if tight else 5e-2) * la[:6].abs().max().item(), (la, lb)
-    d = (flat_params(nets_a) - pb).abs()
-    assert d.max().item() <= 3 * 5e-4 * 3 and (not tight or (d > 0.5 * 1e-4).float().mean().item() < 0.05)
+    ref0 = pa.clone(); dist.broadcast(ref0, 0)
+    assert torch.equal(pa, ref0), "replicas diverged after three eager steps"
+    lb = b.losses.cpu()
+    noise_l = (la[:6] - lc[:6]).abs().max().item()
+    assert (la[:6] - lb[:6]).abs().max().item() <= max((2e-3 if tight else 2e-2) * la[:6].abs().max().item(), 6 * noise_l), (la, lb, lc)
+    d_ab, d_ac = (pa - pb).abs(), (pa - pc).abs()
+    frac_ab, frac_ac = (d_ab > 0.5 * 1e-4).float().mean().item(), (d_ac > 0.5 * 1e-4).float().mean().item()
+    if rank == 0:
+        print(f"[ddp {mode}] 3 steps: fraction of parameters more than 5e-5 apart: eager-graph {frac_ab:.3e}, eager-eager {frac_ac:.3e}; "
+              f"loss |eager-graph| {(la[:6] - lb[:6]).abs().max().item():.2e} (eager-eager {noise_l:.2e})", flush=True)
+    assert d_ab.max().item() <= 3 * 5e-4 * 3 and frac_ab <= max(3 * frac_ac, 0.01), (frac_ab, frac_ac)
+    c.release_graphs()
     a.release_graphs(); b.release_graphs()
     torch.cuda.synchronize()
     dist.barrier()
