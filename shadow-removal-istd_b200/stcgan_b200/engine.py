@@ -223,7 +223,8 @@ class STCGANEngine:
         self._early_d1 = conc and flag("STCGAN_EARLY_D1", "1")        # D1's exchange + Adam share + G-phase passes under G2's forward
         # G2's / G1.ups' / G1.deep's Adam shares underneath the halves of G1's backward: +0.5 % on one GPU, but at N > 1 the
         # HBM-bound Adam kernels slow the NCCL kernels that share G1's backward with them, the serial chain of all-reduces
-        # slips and the last bucket lands late (measured at 8 GPUs: 7.42 ms per step with it, 6.98 ms without) -> single GPU only
+        # slips and the last bucket lands late (measured at 8 GPUs: 7.42 ms per step with it, 6.98 ms without; a hybrid with only
+        # G1's up-conv share moved under the encoder half: 6.70 against 6.61 ms at 2 GPUs) -> single GPU only
         self._adam_early = conc and flag("STCGAN_ADAM_EARLY", "1" if self.world == 1 else "0")
         self._overlap_real = conc and flag("STCGAN_OVERLAP_REAL", "1")  # D2's G-phase real pass next to its fake pass
         self._deep_bucket = flag("STCGAN_DEEP_BUCKET", "1")           # N > 1: G1's deep encoder gradients go on the wire early
