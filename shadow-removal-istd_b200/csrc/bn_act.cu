@@ -543,14 +543,15 @@ bn_bwd_apply_kernel(const T* __restrict__ y, long long P, int H, int W, int C, i
 
 // ---------------------------------------------------------------------------------------------
 // tiny tensors (the innermost U-Net levels: <= 64 pixels x 512 channels): reduce + apply in ONE single-block launch.  The
-// two-pass form costs two dependent ~7 us launches -- pure latency on the backward pass's critical chain; one 1024-thread
-// block reduces in shared memory, derives the coefficients and applies them (the second read of y / g hits L1/L2).  One SM
-// streams ~100 GB/s, so this only wins below ~0.5 MB of traffic: measured on B200, 256-pixel tensors (1.8 MB) took 30 us
-// this way against 14 us in two passes, hence the 64-pixel bound.  Same arithmetic as the two-pass kernels: fp32 partial sums per
-// thread, fp64 across the block.
+// two-pass form costs two dependent ~7 us launches -- pure latency on the backward pass's critical chain; one 512-thread
+// block (<= 128 registers per thread: at 1024 threads the 64-register cap made the pixel loop spill) reduces in shared
+// memory, derives the coefficients and applies them (the second read of y / g hits L1/L2).  One SM streams ~100 GB/s, so
+// this only wins below ~0.5 MB of traffic: measured on B200, 256-pixel tensors (1.8 MB) took 30 us this way against 14 us
+// in two passes, hence the 64-pixel bound.  Same arithmetic as the two-pass kernels: fp32 partial sums per thread, fp64
+// across the block.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 bn_bwd_small_kernel(const T* __restrict__ y, long long P, int H, int W, int C, int ldy,
                     const float* __restrict__ ss, const float* __restrict__ mi, const float* __restrict__ gamma,
                     int HC, int WC, const T* __restrict__ g1, int ldg1, int act1, const T* __restrict__ g2, int ldg2, int act2,
@@ -773,12 +774,12 @@ int bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int l
                      const float* gamma, int HC, int WC, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
                      int act2, void* dy, int lddy, float* dgamma, float* dbeta, cudaStream_t st) {
   const long long P = (long long)N * H * W;
-  if (dtype != STCGAN_BF16 || C % VEC != 0 || C > 1024 || P * C > 64LL * 512 || P < 1) return STCGAN_EUNSUPPORTED;
+  if (dtype != STCGAN_BF16 || C % VEC != 0 || C > 4096 || P * C > 64LL * 512 || P < 1) return STCGAN_EUNSUPPORTED;
   if (!ss || !mi || !gamma || !g1 || !dy || !vec_ok(dtype, y, ldy) || !vec_ok(dtype, g1, ldg1) || !vec_ok(dtype, g2, ldg2) ||
       !vec_ok(dtype, dy, lddy))
     return STCGAN_EINVAL;
-  int cv = C / VEC; if (cv > 1024) cv = 1024;
-  int rows = 1024 / cv; if (rows < 1) rows = 1;
+  int cv = C / VEC; if (cv > 512) cv = 512;
+  int rows = 512 / cv; if (rows < 1) rows = 1;
   if ((long long)rows > P) rows = (int)P;
   const size_t smem = ((size_t)2 * rows * C + 3 * C) * sizeof(float);
   if (smem > 200 * 1024) return STCGAN_EUNSUPPORTED;
@@ -788,7 +789,7 @@ int bn_act_bwd_small(int dtype, const void* y, int N, int H, int W, int C, int l
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  launch_k(bn_bwd_small_kernel<__nv_bfloat16>, 1, 1024, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi,
+  launch_k(bn_bwd_small_kernel<__nv_bfloat16>, 1, 512, smem, st, static_cast<const __nv_bfloat16*>(y), P, H, W, C, ldy, ss, mi,
            gamma, HC, WC, static_cast<const __nv_bfloat16*>(g1), ldg1, act1, static_cast<const __nv_bfloat16*>(g2), ldg2, act2,
            static_cast<__nv_bfloat16*>(dy), lddy, dgamma, dbeta, cv, rows, 1.0 / (double)P);
   return finish_launch();

@@ -433,8 +433,12 @@ def out_act_bwd(act, out_nchw, dout_nchw, dtype, cpad=None, border=0):
     return g
 
 
+# single-launch BatchNorm backward for tiny tensors (stcgan_bn_act_bwd_small): OPT-IN (STCGAN_SMALL_BN=1).  Measured on B200 it
+# does not pay: the four 64-pixel BatchNorm layers of a train step took 6 us longer each in one single-block launch than in the
+# two-pass form (6.16-6.19 against 6.12 ms per step) -- one SM cannot hide three dependent global round trips any better than
+# two small grids do.
 SMALL_BN_ELEMS = 64 * 512
-_SMALL_BN = _os.environ.get("STCGAN_SMALL_BN", "1") != "0"
+_SMALL_BN = _os.environ.get("STCGAN_SMALL_BN", "0") == "1"
 
 KIND_L1, KIND_MSE, KIND_BCE = 0, 1, 2
 

@@ -271,6 +271,14 @@ def test_batchnorm_act_forward_backward(cuda, lib, mode, shape, training):
     assert rel_err(op.gbeta, ref_bn.bias.grad) < (1e-4 if mode == "fp32" else 2e-2)
 
 
+def test_batchnorm_backward_single_launch_variant(cuda, lib, monkeypatch):
+    """the opt-in single-launch backward for tiny tensors (stcgan_bn_act_bwd_small) against the same torch reference"""
+    from stcgan_b200 import ops
+    monkeypatch.setattr(ops, "_SMALL_BN", True)
+    test_batchnorm_act_forward_backward(cuda, lib, "bf16", (16, 2, 2, 512), True)
+    test_batchnorm_act_forward_backward(cuda, lib, "bf16", (2, 3, 5, 64), True)
+
+
 def test_batchnorm_single_value_raises(cuda, lib):
     from stcgan_b200 import nets
     from stcgan_b200._lib import ACT_RELU
