@@ -123,6 +123,21 @@ def test_library_exports_every_declared_symbol(lib):
     assert b"invalid argument" in lib.stcgan_error_string(-1) and lib.stcgan_error_string(0) == b"ok"
 
 
+def test_ctypes_signatures_match_header_prototypes():
+    """every prototype of include/stcgan_b200.h has as many parameters as the ctypes binding passes (a drift between the
+    header and stcgan_b200/_lib.py would corrupt the stack silently), and every one cites what it replaces nearby"""
+    from stcgan_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "stcgan_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(stcgan_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", code, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
+    assert hdr.count(".py:") >= 30          # reference call sites (file:line) are cited throughout the header
+
+
 def test_library_argument_validation_without_gpu(lib):
     """bad arguments are rejected on the host before any launch (error convention: negative code, no throw)."""
     assert lib.stcgan_tapconv(99, 0, 0, 1, 1, 4, 4, 8, 8, 1, None, 0, 1, 2, 2, 8, 8, 0, None, 0, None) == -1      # unknown geometry
